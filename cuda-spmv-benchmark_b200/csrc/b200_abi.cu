@@ -1,0 +1,512 @@
+// b200_abi.cu -- extern "C" launchers: the only translation unit that includes kernel headers.
+// See include/b200_kernels.h for the contract of every entry point.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/b200_kernels.h"
+#include "cg_kernels.cuh"
+#include "csr_ell.cuh"
+#include "generate.cuh"
+#include "stencil5.cuh"
+#include "stencil_layout.h"
+
+using namespace b200;
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+
+static int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+        return (e == cudaErrorNoKernelImageForDevice || e == cudaErrorNoDevice ||
+                e == cudaErrorInsufficientDriver)
+                   ? B200_ENODEV
+                   : B200_ECUDA;
+    }
+    return B200_OK;
+}
+
+extern "C" const char* b200_version(void) { return "b200-spmv-cg 0.1 (sm_100a)"; }
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" unsigned long long b200_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// STENCIL5
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Variant {
+    int cols, warps, stages;
+    const char* info;
+};
+// keep in sync with the dispatch switch below
+const Variant kVariants[] = {
+    {2, 4, 4, "v0: 64-col strips (2 cols/lane), 4 warps/CTA, 4-stage ring"},
+    {1, 4, 4, "v1: 32-col strips (1 col/lane), 4 warps/CTA, 4-stage ring"},
+    {2, 8, 4, "v2: 64-col strips, 8 warps/CTA, 4-stage ring"},
+    {4, 4, 3, "v3: 128-col strips (4 cols/lane), 4 warps/CTA, 3-stage ring"},
+    {2, 4, 6, "v4: 64-col strips, 4 warps/CTA, 6-stage ring"},
+    {2, 2, 4, "v5: 64-col strips, 2 warps/CTA, 4-stage ring"},
+    {4, 2, 4, "v6: 128-col strips, 2 warps/CTA, 4-stage ring"},
+    {1, 8, 6, "v7: 32-col strips, 8 warps/CTA, 6-stage ring"},
+};
+const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+const int kDefaultRowsPerItem = 32;
+
+struct Geometry {
+    Stencil5Args a;
+    int grid;
+    int threads;
+    size_t smem;
+};
+
+int build_geometry(const b200_band* b, const double* x, Geometry* g) {
+    if (!b || !x) return fail(B200_EINVAL, "stencil5: NULL band or vector");
+    if (b->grid_size < 1 || b->n_local < 0 || b->row_offset < 0) return fail(B200_EINVAL, "stencil5: bad geometry");
+    const long long n = b->grid_size, N = n * n;
+    if (b->row_offset + b->n_local > N) return fail(B200_EINVAL, "stencil5: band exceeds grid_size^2 rows");
+    if (!b->d_values || !b->d_col_idx) return fail(B200_EINVAL, "stencil5: NULL matrix arrays");
+    if (b->layout == 0 && !b->d_row_ptr) return fail(B200_EINVAL, "stencil5: CSR layout needs row_ptr");
+    if (((uintptr_t)b->d_values & 15) != 0) return fail(B200_EINVAL, "stencil5: values must be 16-byte aligned");
+    const int v = (b->variant >= 0 && b->variant < kNumVariants) ? b->variant : 0;
+    const Variant& V = kVariants[v];
+    Stencil5Args& a = g->a;
+    memset(&a, 0, sizeof a);
+    a.row_ptr = b->layout == 0 ? b->d_row_ptr : nullptr;
+    a.col_idx = b->d_col_idx;
+    a.values = b->d_values;
+    a.values_len = b->values_len;
+    a.x = x;
+    a.halo_prev = b->d_halo_prev;
+    a.halo_next = b->d_halo_next;
+    a.row_offset = b->row_offset;
+    a.n_local = b->n_local;
+    a.n = (int)n;
+    if (b->layout == 0) {
+        // element(i,j) = nnz_before(full CSR) - slice start = (4n-2) + (i-1)(5n-2) + 4 + 5(j-1) - base
+        a.base0 = -n - 1 - stencil5_nnz_before(b->row_offset, n);
+        a.row_stride = 5 * n - 2;
+    } else {
+        a.base0 = -5 * b->row_offset;
+        a.row_stride = 5 * n;
+    }
+    const long long first = b->row_offset, last = b->row_offset + b->n_local - 1;
+    long long i_first = first / n, i_last = b->n_local > 0 ? last / n : -1;
+    if (i_first < 1) i_first = 1;
+    if (i_last > n - 2) i_last = n - 2;
+    const int W = 32 * V.cols;
+    int R = b->rows_per_item > 0 ? b->rows_per_item : kDefaultRowsPerItem;
+    a.rows_per_item = R;
+    a.i_first = (int)i_first;
+    a.i_last = (int)i_last;
+    if (i_last >= i_first && n > 2) {
+        a.n_strips = (int)((n - 2 + W - 1) / W);
+        a.n_chunks = (int)((i_last - i_first + 1 + R - 1) / R);
+        a.ctas_per_chunk = (a.n_strips + V.warps - 1) / V.warps;
+        a.n_interior_ctas = a.n_chunks * a.ctas_per_chunk;
+    } else {
+        a.n_strips = a.n_chunks = a.n_interior_ctas = 0;
+        a.ctas_per_chunk = 1;
+    }
+    a.n_boundary_rows = (n == 1) ? 1 : (int)(4 * n - 4);
+    a.flag_prev = b->d_flag_prev;
+    a.flag_next = b->d_flag_next;
+    a.epoch = b->epoch;
+    g->threads = V.warps * 32;
+    const int nb = (a.n_boundary_rows + g->threads - 1) / g->threads;
+    g->grid = a.n_interior_ctas + nb;
+    g->smem = (size_t)V.warps * V.stages * (5 * W + 2) * 8 + (size_t)V.warps * V.stages * 8;
+    return B200_OK;
+}
+
+template <int MODE, int COLS, int WARPS, int STAGES, bool CG>
+int launch_one(const Geometry& g, cudaStream_t s) {
+    auto k = stencil5_kernel<MODE, COLS, WARPS, STAGES, CG>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "stencil5: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction) ? B200_ENODEV
+                                                                                                 : B200_ECUDA;
+        }
+        attr_set = true;
+    }
+    k<<<g.grid, g.threads, g.smem, s>>>(g.a);
+    return check_launch("stencil5_kernel");
+}
+
+template <int MODE, bool CG>
+int launch_variant(int v, const Geometry& g, cudaStream_t s) {
+    switch (v) {
+        case 1: return launch_one<MODE, 1, 4, 4, CG>(g, s);
+        case 2: return launch_one<MODE, 2, 8, 4, CG>(g, s);
+        case 3: return launch_one<MODE, 4, 4, 3, CG>(g, s);
+        case 4: return launch_one<MODE, 2, 4, 6, CG>(g, s);
+        case 5: return launch_one<MODE, 2, 2, 4, CG>(g, s);
+        case 6: return launch_one<MODE, 4, 2, 4, CG>(g, s);
+        case 7: return launch_one<MODE, 1, 8, 6, CG>(g, s);
+        default: return launch_one<MODE, 2, 4, 4, CG>(g, s);
+    }
+}
+
+template <int MODE>
+int launch_stencil(const b200_band* b, Geometry& g, cudaStream_t s) {
+    if (g.grid == 0) return B200_OK;
+    const int v = (b->variant >= 0 && b->variant < kNumVariants) ? b->variant : 0;
+    // peer-written halos must be read through L2 (ld.global.cg); single-GPU uses the read-only path
+    const bool cg = (b->d_halo_prev != nullptr || b->d_halo_next != nullptr);
+    return cg ? launch_variant<MODE, true>(v, g, s) : launch_variant<MODE, false>(v, g, s);
+}
+
+}  // namespace
+
+extern "C" const char* b200_stencil5_variant_info(int v) {
+    return (v >= 0 && v < kNumVariants) ? kVariants[v].info : nullptr;
+}
+
+extern "C" int b200_stencil5_num_partials(const b200_band* band) {
+    Geometry g;
+    static const double dummy = 0;
+    if (build_geometry(band, &dummy, &g) != B200_OK) return -1;
+    return g.grid;
+}
+
+extern "C" int b200_stencil5_spmv(const b200_band* band, const double* d_x, double* d_y, b200_stream stream) {
+    Geometry g;
+    int rc = build_geometry(band, d_x, &g);
+    if (rc) return rc;
+    if (!d_y) return fail(B200_EINVAL, "stencil5: NULL y");
+    g.a.y = d_y;
+    return launch_stencil<ST_PLAIN>(band, g, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_stencil5_csr(const int* d_row_ptr, const int* d_col_idx, const double* d_values,
+                                      const double* d_x, double* d_y, int N, int grid_size, b200_stream stream) {
+    if ((long long)grid_size * grid_size != N) return fail(B200_EINVAL, "stencil5-csr: N != grid_size^2");
+    b200_band b;
+    memset(&b, 0, sizeof b);
+    b.d_row_ptr = d_row_ptr; b.d_col_idx = d_col_idx; b.d_values = d_values;
+    b.values_len = stencil5_nnz(grid_size);
+    b.row_offset = 0; b.n_local = N; b.grid_size = grid_size; b.layout = 0;
+    return b200_stencil5_spmv(&b, d_x, d_y, stream);
+}
+
+extern "C" int b200_spmv_stencil5_halo(const int* d_row_ptr, const int* d_col_idx, const double* d_values,
+                                       const double* d_x_local, const double* d_x_halo_prev,
+                                       const double* d_x_halo_next, double* d_y, int n_local, long long row_offset,
+                                       long long N, int grid_size, b200_stream stream) {
+    if ((long long)grid_size * grid_size != N) return fail(B200_EINVAL, "stencil5-halo: N != grid_size^2");
+    b200_band b;
+    memset(&b, 0, sizeof b);
+    b.d_row_ptr = d_row_ptr; b.d_col_idx = d_col_idx; b.d_values = d_values;
+    b.values_len = stencil5_nnz_before(row_offset + n_local, grid_size) - stencil5_nnz_before(row_offset, grid_size);
+    b.row_offset = row_offset; b.n_local = n_local; b.grid_size = grid_size; b.layout = 0;
+    b.d_halo_prev = d_x_halo_prev; b.d_halo_next = d_x_halo_next;
+    return b200_stencil5_spmv(&b, d_x_local, d_y, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic CSR / ELLPACK
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kCsrThreads = 256;
+
+int launch_csr(const CsrArgs& a, cudaStream_t s) {
+    if (a.n_rows == 0) return B200_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(csr_adaptive_kernel<kCsrThreads>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "csr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return B200_ENODEV;
+        }
+        attr_set = true;
+    }
+    const long long blocks = (a.n_rows + a.rows_per_block - 1) / a.rows_per_block;
+    if (blocks > 2147483647LL) return fail(B200_EINVAL, "csr: too many row blocks");
+    csr_adaptive_kernel<kCsrThreads><<<(unsigned)blocks, kCsrThreads, (size_t)a.window * 16, s>>>(a);
+    return check_launch("csr_adaptive_kernel");
+}
+}  // namespace
+
+extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long long nnz, b200_csr_plan* plan,
+                                   b200_stream stream) {
+    if (!plan || (!d_row_ptr && n_rows > 0)) return fail(B200_EINVAL, "csr plan: NULL argument");
+    memset(plan, 0, sizeof *plan);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* d_bins = nullptr;
+    if (cudaMalloc(&d_bins, 34 * sizeof(unsigned long long)) != cudaSuccess) return fail(B200_ENOMEM, "csr plan: cudaMalloc");
+    cudaMemsetAsync(d_bins, 0, 34 * sizeof(unsigned long long), s);
+    if (n_rows > 0) {
+        long long blocks = (n_rows + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        row_length_histogram_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_row_ptr, n_rows, d_bins, d_bins + 33);
+        int rc = check_launch("row_length_histogram_kernel");
+        if (rc) { cudaFree(d_bins); return rc; }
+    }
+    unsigned long long h[34];
+    cudaError_t e = cudaMemcpyAsync(h, d_bins, sizeof h, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_bins);
+    if (e != cudaSuccess) return fail(B200_ECUDA, "csr plan: %s", cudaGetErrorString(e));
+    memcpy(plan->hist, h, 33 * sizeof(unsigned long long));
+    plan->max_row_len = h[33];
+    plan->mean_row_len = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
+    // Block shape from the histogram: the window holds rows_per_block rows of the 95th-percentile
+    // length; blocks whose rows are longer than the window fall back to warp-per-row at run time.
+    unsigned long long acc = 0, target = (unsigned long long)(0.95 * (double)n_rows);
+    int p95_bin = 0;
+    for (int b = 0; b < 33; b++) { acc += h[b]; if (acc >= target) { p95_bin = b; break; } }
+    long long p95_len = 1LL << p95_bin;
+    if (p95_len > (long long)plan->max_row_len && plan->max_row_len > 0) p95_len = (long long)plan->max_row_len;
+    int window = 3072;  // 48 KB of shared memory per CTA (values + gathered x) -> 4 CTAs / SM
+    long long rpb = window / (p95_len > 0 ? p95_len : 1);
+    if (rpb > 512) rpb = 512;
+    if (rpb < 8) rpb = 8;
+    plan->rows_per_block = (int)rpb;
+    plan->window = window;
+    return B200_OK;
+}
+
+extern "C" int b200_spmv_csr(const b200_csr_plan* plan, const int* d_row_ptr, const int* d_col_idx,
+                             const double* d_values, const double* d_x, double* d_y, long long n_rows, double alpha,
+                             double beta, b200_stream stream) {
+    if (!plan || !d_row_ptr || !d_x || !d_y) return fail(B200_EINVAL, "csr: NULL argument");
+    CsrArgs a;
+    a.row_ptr = d_row_ptr; a.col_idx = d_col_idx; a.values = d_values; a.x = d_x; a.y = d_y;
+    a.n_rows = n_rows; a.ell_width = 0; a.rows_per_block = plan->rows_per_block; a.window = plan->window;
+    a.alpha = alpha; a.beta = beta;
+    return launch_csr(a, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
+                                 long long n_rows, int width, double alpha, double beta, b200_stream stream) {
+    if (!d_indices || !d_values || !d_x || !d_y) return fail(B200_EINVAL, "ellpack: NULL argument");
+    if (width < 1 || width > 1000) return fail(B200_EINVAL, "ellpack: width outside [1, MAX_WIDTH]");
+    CsrArgs a;
+    a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
+    a.n_rows = n_rows; a.ell_width = width; a.window = 3072;
+    int rpb = a.window / width;
+    if (rpb > 512) rpb = 512;
+    if (rpb < 1) rpb = 1;
+    a.rows_per_block = rpb;
+    a.alpha = alpha; a.beta = beta;
+    return launch_csr(a, (cudaStream_t)stream);
+}
+
+extern "C" int b200_spmv_stencil5_ellpack(const double* d_values, const int* d_col_indices, const double* d_x,
+                                          double* d_y, int num_rows, int width, double alpha, double beta,
+                                          int grid_size, b200_stream stream) {
+    // fast path: the closed-form interior kernel on the width-5 layout when it is a plain product
+    if (width == 5 && alpha == 1.0 && beta == 0.0 && (long long)grid_size * grid_size == num_rows) {
+        b200_band b;
+        memset(&b, 0, sizeof b);
+        b.d_col_idx = d_col_indices; b.d_values = d_values; b.values_len = 5LL * num_rows;
+        b.row_offset = 0; b.n_local = num_rows; b.grid_size = grid_size; b.layout = 1;
+        return b200_stencil5_spmv(&b, d_x, d_y, stream);
+    }
+    return b200_spmv_ellpack(d_col_indices, d_values, d_x, d_y, num_rows, width, alpha, beta, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused CG steps
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t b200_cg_scalars_bytes(void) { return sizeof(CGScalars); }
+extern "C" size_t b200_cg_status_bytes(void) { return sizeof(CGStatus); }
+extern "C" size_t b200_xchg_bytes(void) { return sizeof(XchgArea); }
+extern "C" size_t b200_xchg_flag_prev_offset(void) { return offsetof(XchgArea, halo_flag_prev); }
+extern "C" size_t b200_xchg_flag_next_offset(void) { return offsetof(XchgArea, halo_flag_next); }
+
+namespace {
+constexpr int kBlas1Ctas = 148 * 8;  // 8 resident 256-thread CTAs per SM, one wave
+inline int blas1_grid(long long n, int vec) {
+    const long long tile = 256LL * vec * 4;
+    long long need = (n + tile - 1) / tile;
+    if (need < 1) need = 1;
+    return (int)(need < kBlas1Ctas ? need : kBlas1Ctas);
+}
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+}  // namespace
+
+extern "C" int b200_cg_max_partials(const b200_band* band) {
+    int n = b200_stencil5_num_partials(band);
+    if (n < 0) return n;
+    return n > kBlas1Ctas ? n : kBlas1Ctas;
+}
+
+extern "C" int b200_cg_residual_init(const b200_band* band, const double* d_x, const double* d_b, double* d_r,
+                                     double* d_p, double* d_partials, void* d_scalars, b200_stream stream) {
+    Geometry g;
+    int rc = build_geometry(band, d_x, &g);
+    if (rc) return rc;
+    if (!d_b || !d_r || !d_p || !d_partials) return fail(B200_EINVAL, "cg_residual_init: NULL argument");
+    g.a.y = d_r; g.a.y2 = d_p; g.a.b = d_b; g.a.partials = d_partials;
+    if (d_scalars) g.a.error_word = &static_cast<CGScalars*>(d_scalars)->error;
+    return launch_stencil<ST_RESID>(band, g, (cudaStream_t)stream);
+}
+
+extern "C" int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double* d_Ap, double* d_partials,
+                                const void* d_scalars, b200_stream stream) {
+    Geometry g;
+    int rc = build_geometry(band, d_p, &g);
+    if (rc) return rc;
+    if (!d_Ap || !d_partials) return fail(B200_EINVAL, "cg_spmv_dot: NULL argument");
+    g.a.y = d_Ap; g.a.partials = d_partials;
+    if (d_scalars) {
+        g.a.converged = &static_cast<const CGScalars*>(d_scalars)->converged;
+        g.a.error_word = &const_cast<CGScalars*>(static_cast<const CGScalars*>(d_scalars))->error;
+    }
+    return launch_stencil<ST_DOT>(band, g, (cudaStream_t)stream);
+}
+
+extern "C" int b200_cg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
+                                 double* d_x, double* d_r, double* d_partials, int* n_partials_out,
+                                 b200_stream stream) {
+    if (!d_scalars || !d_p || !d_Ap || !d_x || !d_r || !d_partials) return fail(B200_EINVAL, "cg_update_xr: NULL argument");
+    const bool v2 = aligned16(d_p) && aligned16(d_Ap) && aligned16(d_x) && aligned16(d_r);
+    const int grid = blas1_grid(n, v2 ? 2 : 1);
+    if (n_partials_out) *n_partials_out = grid;
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    if (v2) cg_update_xr_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_p, d_Ap, d_x, d_r, d_partials);
+    else cg_update_xr_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_p, d_Ap, d_x, d_r, d_partials);
+    return check_launch("cg_update_xr_kernel");
+}
+
+extern "C" int b200_cg_update_p(long long n, const void* d_scalars, const double* d_r, double* d_p,
+                                b200_stream stream) {
+    if (!d_scalars || !d_r || !d_p) return fail(B200_EINVAL, "cg_update_p: NULL argument");
+    const bool v2 = aligned16(d_r) && aligned16(d_p);
+    const int grid = blas1_grid(n, v2 ? 2 : 1);
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    if (v2) cg_update_p_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_r, d_p);
+    else cg_update_p_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_r, d_p);
+    return check_launch("cg_update_p_kernel");
+}
+
+extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
+                              void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
+                              uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream) {
+    if (!d_partials || n_partials < 0) return fail(B200_EINVAL, "cg_reduce: bad partials");
+    if (which != RED_SUM && !d_scalars) return fail(B200_EINVAL, "cg_reduce: NULL scalars");
+    if (which == RED_SUM && !d_out) return fail(B200_EINVAL, "cg_reduce: NULL out");
+    if (world < 1 || world > B200_MAX_RANKS || rank < 0 || rank >= world) return fail(B200_EINVAL, "cg_reduce: bad rank/world");
+    if (world > 1 && !d_peer_xchg) return fail(B200_EINVAL, "cg_reduce: NULL peer table");
+    if (phases != 3 && !d_stash) return fail(B200_EINVAL, "cg_reduce: split phases need a stash");
+    ReduceArgs a;
+    memset(&a, 0, sizeof a);
+    a.partials = d_partials; a.n_partials = n_partials; a.which = which; a.phases = phases; a.tol = tol;
+    a.sc = static_cast<CGScalars*>(d_scalars);
+    a.status = static_cast<CGStatus*>(h_status_mapped);
+    a.out = d_out; a.rank = rank; a.world = world; a.epoch = epoch; a.stash = d_stash;
+    if (world > 1) {
+        for (int r = 0; r < world; r++) a.peer_xchg[r] = static_cast<XchgArea*>(d_peer_xchg[r]);
+        a.my_xchg = a.peer_xchg[rank];
+    }
+    cg_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("cg_reduce_kernel");
+}
+
+extern "C" int b200_dot_partials(long long n, const void* d_scalars, const double* d_x, const double* d_y,
+                                 double* d_partials, int* n_partials_out, b200_stream stream) {
+    if (!d_x || !d_y || !d_partials) return fail(B200_EINVAL, "dot_partials: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    if (n_partials_out) *n_partials_out = grid;
+    dot_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_x, d_y,
+                                                                d_partials);
+    return check_launch("dot_partials_kernel");
+}
+
+extern "C" int b200_residual_init_generic(long long n, const double* d_b, const double* d_Ap, double* d_r,
+                                          double* d_p, double* d_partials, int* n_partials_out, b200_stream stream) {
+    if (!d_b || !d_Ap || !d_r || !d_p || !d_partials) return fail(B200_EINVAL, "residual_init: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    if (n_partials_out) *n_partials_out = grid;
+    residual_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_b, d_Ap, d_r, d_p, d_partials);
+    return check_launch("residual_init_kernel");
+}
+
+extern "C" int b200_checksum_partials(long long n, const double* d_x, double* d_psum, double* d_psq,
+                                      int* n_partials_out, b200_stream stream) {
+    if (!d_x || !d_psum || !d_psq) return fail(B200_EINVAL, "checksum: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    if (n_partials_out) *n_partials_out = grid;
+    checksum_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_x, d_psum, d_psq);
+    return check_launch("checksum_partials_kernel");
+}
+
+extern "C" int b200_halo_push(const double* d_v_local, long long n_local, int halo, double* d_dst_prev,
+                              double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next, uint32_t epoch,
+                              void* d_my_xchg, const void* d_scalars, b200_stream stream) {
+    if (!d_v_local || !d_my_xchg || halo < 1 || n_local < halo) return fail(B200_EINVAL, "halo_push: bad argument");
+    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "halo_push: NULL flag");
+    HaloPushArgs a;
+    a.v_local = d_v_local; a.n_local = n_local; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
+    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
+    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
+    a.sc = static_cast<const CGScalars*>(d_scalars);
+    const int per_dir = 8;
+    halo_push_kernel<<<2 * per_dir, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("halo_push_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side matrix construction
+// ------------------------------------------------------------------------------------------------
+extern "C" long long b200_stencil5_nnz_before(long long row, long long grid_size) {
+    return stencil5_nnz_before(row, grid_size);
+}
+
+static unsigned gen_grid(long long n) {
+    long long b = (n + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148LL * 32) b = 148LL * 32;
+    return (unsigned)b;
+}
+
+extern "C" int b200_gen_stencil5_csr(int grid_size, long long row_offset, long long n_local, double center,
+                                     double neighbour, int* d_row_ptr, int* d_col_idx, double* d_values,
+                                     b200_stream stream) {
+    if (!d_row_ptr || !d_col_idx || !d_values || grid_size < 1) return fail(B200_EINVAL, "gen csr: bad argument");
+    if ((long long)grid_size * grid_size > 2147483647LL) return fail(B200_EINVAL, "gen csr: 32-bit column ids overflow");
+    gen_stencil5_csr_kernel<<<gen_grid(n_local + 1), 256, 0, (cudaStream_t)stream>>>(grid_size, row_offset, n_local, center,
+                                                                                    neighbour, d_row_ptr, d_col_idx, d_values);
+    return check_launch("gen_stencil5_csr_kernel");
+}
+
+extern "C" int b200_gen_stencil5_ellpack(int grid_size, long long row_offset, long long n_local, double center,
+                                         double neighbour, int* d_indices, double* d_values, b200_stream stream) {
+    if (!d_indices || !d_values || grid_size < 1) return fail(B200_EINVAL, "gen ell: bad argument");
+    gen_stencil5_ell_kernel<<<gen_grid(n_local), 256, 0, (cudaStream_t)stream>>>(grid_size, row_offset, n_local, center,
+                                                                                neighbour, d_indices, d_values);
+    return check_launch("gen_stencil5_ell_kernel");
+}
+
+extern "C" int b200_gen_stencil5_entries(int grid_size, long long row_offset, long long n_local, double center,
+                                         double neighbour, void* d_entries, b200_stream stream) {
+    if (!d_entries || grid_size < 1) return fail(B200_EINVAL, "gen entries: bad argument");
+    gen_stencil5_entries_kernel<<<gen_grid(n_local), 256, 0, (cudaStream_t)stream>>>(
+        grid_size, row_offset, n_local, center, neighbour, static_cast<EntryPOD*>(d_entries));
+    return check_launch("gen_stencil5_entries_kernel");
+}
+
+extern "C" int b200_fill(double* d_p, long long n, double value, b200_stream stream) {
+    if (!d_p && n > 0) return fail(B200_EINVAL, "fill: NULL");
+    if (n <= 0) return B200_OK;
+    fill_kernel<<<gen_grid(n), 256, 0, (cudaStream_t)stream>>>(d_p, n, value);
+    return check_launch("fill_kernel");
+}

@@ -1,0 +1,372 @@
+// cg_kernels.cuh -- fused CG building blocks for sm_100a.
+//
+// Reference sequence per iteration (src/solvers/cg_solver.cu:538-638): SpMV, dot_kernel +
+// final_sum_kernel, scalar_divide, axpy, axpy_sub, dot + final_sum, check_convergence, blocking
+// 4-byte D2H, scalar_divide, update_p, 8-byte D2D  -- 11 launches, 152 B/row, one host sync.
+// Here: K1 (SpMV + p.Ap partials, stencil5.cuh) -> R (fixed-order final sum, alpha) ->
+// K2 (x += alpha p, r -= alpha Ap, r.r partials) -> R (final sum, convergence, beta) ->
+// K3 (p = r + beta p)  -- 5 launches, 128 B/row, no host sync (scalars stay on the device, the
+// host polls a pinned status word a few iterations behind).
+//
+// Determinism: every partial sum has a fixed owner (CTA id), every CTA sums in a fixed order,
+// the final pass adds partials in index order and ranks in rank order, so iteration counts are
+// reproducible run to run and identical on every GPU of a multi-GPU solve.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+#define B200_MAX_RANKS 16
+
+// device-resident CG scalars (one per rank)
+struct CGScalars {
+    double rr_old;
+    double rr_new;
+    double pAp;
+    double alpha;
+    double beta;
+    double b_norm;    // sqrt(r0.r0): the reference's "b_norm" (cg_solver.cu:527-528)
+    double residual;  // sqrt(rr_new) of the last checked iteration
+    int converged;
+    int iterations;   // completed iterations (counts the converging one, cg_solver.cu:619)
+    int error;        // a peer-flag wait timed out: later waits return at once
+};
+
+// host-visible mirror (pinned, mapped), written by the reduce kernel after every r.r
+struct CGStatus {
+    volatile int iterations;
+    volatile int converged;
+    volatile double residual;
+    volatile double b_norm;
+    volatile int error;  // flag-wait timeout in a peer exchange
+};
+
+// exchange area of one rank, in that rank's device memory, written by its peers over NVLink
+struct XchgArea {
+    uint64_t slots[2][B200_MAX_RANKS][2];  // LL words: (epoch << 32 | 32 data bits) x 2 per double
+    uint32_t halo_flag_prev;               // epoch of the last halo written by rank-1
+    uint32_t halo_flag_next;               // epoch of the last halo written by rank+1
+    uint32_t push_count[2];                // local: CTAs done with the halo push (prev, next)
+    uint32_t pad[26];
+};
+
+enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3 };
+enum { RED_PUSH = 1, RED_COMBINE = 2 };
+
+struct ReduceArgs {
+    const double* partials;
+    int n_partials;
+    int which;   // RED_*
+    int phases;  // RED_PUSH | RED_COMBINE
+    double tol;
+    CGScalars* sc;
+    CGStatus* status;  // may be NULL
+    double* out;       // RED_SUM: result
+    // multi-rank
+    int rank, world;
+    uint32_t epoch;
+    XchgArea* my_xchg;
+    XchgArea* peer_xchg[B200_MAX_RANKS];
+    double* stash;  // local: my partial sum between PUSH and COMBINE launches
+};
+
+// One CTA of 1024 threads.  Fixed-order final sum of the per-CTA partials, optional rank
+// exchange (LL protocol: data and epoch travel in the same 8-byte store, so no fence), then the
+// scalar recurrences that the reference spreads over scalar_divide_kernel /
+// check_convergence_kernel / a D2D copy (cg_solver.cu:414-431,560,594-637).
+__global__ void __launch_bounds__(1024) cg_reduce_kernel(const ReduceArgs a) {
+    __shared__ double scratch[32];
+    __shared__ double rank_sum[B200_MAX_RANKS];
+    __shared__ double local_total;
+    CGScalars* sc = a.sc;
+    if (a.which != RED_SUM && sc->converged) return;
+
+    const int t = threadIdx.x;
+    if (a.phases & RED_PUSH) {
+        double v = 0.0;
+        for (int i = t; i < a.n_partials; i += 1024) v += a.partials[i];
+        v = block_sum(v, scratch);
+        if (t == 0) { local_total = v; if (a.stash) *a.stash = v; }
+        __syncthreads();
+        if (a.world > 1 && t < a.world) {
+            const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
+            const uint64_t tag = (uint64_t)a.epoch << 32;
+            uint64_t* dst = a.peer_xchg[t]->slots[a.epoch & 1][a.rank];
+            st_volatile_u64(dst, tag | (bits & 0xffffffffull));
+            st_volatile_u64(dst + 1, tag | (bits >> 32));
+        }
+    } else if (t == 0) {
+        local_total = *a.stash;
+    }
+    if (!(a.phases & RED_COMBINE)) return;
+    __syncthreads();
+
+    double total = local_total;
+    if (a.world > 1) {
+        if (t < a.world) {
+            const uint64_t* src = a.my_xchg->slots[a.epoch & 1][t];
+            const uint64_t t0 = globaltimer_ns();
+            const bool dead = (sc != nullptr && sc->error != 0);
+            uint64_t w0, w1;
+            for (;;) {
+                w0 = ld_volatile_u64(src);
+                w1 = ld_volatile_u64(src + 1);
+                if ((uint32_t)(w0 >> 32) == a.epoch && (uint32_t)(w1 >> 32) == a.epoch) break;
+                if (dead || globaltimer_ns() - t0 > 8000000000ull) {  // 8 s: report, never hang
+                    if (sc) sc->error = 1;
+                    if (a.status) a.status->error = 1;
+                    break;
+                }
+            }
+            rank_sum[t] = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+        }
+        __syncthreads();
+        if (t == 0) {
+            total = 0.0;
+            for (int r = 0; r < a.world; r++) total += rank_sum[r];  // rank order: same on every GPU
+        }
+    }
+    if (t != 0) return;
+
+    if (a.which == RED_SUM) {
+        *a.out = total;
+    } else if (a.which == RED_RR0) {
+        sc->rr_old = total;
+        sc->b_norm = sqrt(total);
+        sc->residual = sc->b_norm;
+        if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
+    } else if (a.which == RED_PAP) {
+        sc->pAp = total;
+        sc->alpha = sc->rr_old / total;
+    } else {  // RED_RR
+        sc->rr_new = total;
+        const double res = sqrt(total);
+        sc->residual = res;
+        const int it = sc->iterations + 1;
+        sc->iterations = it;
+        const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
+        if (conv) {
+            sc->converged = 1;
+        } else {
+            sc->beta = total / sc->rr_old;
+            sc->rr_old = total;
+        }
+        if (a.status) {
+            a.status->residual = res;
+            a.status->iterations = it;
+            a.status->converged = conv;
+            __threadfence_system();
+        }
+    }
+}
+
+// K2: x += alpha p ; r -= alpha Ap ; partials[cta] = sum r^2 over the CTA's tiles.
+// reference: axpy_kernel_device + axpy_sub_kernel_device + dot_kernel (cg_solver.cu:59-78,110-132)
+// contracted the same way (fma(alpha,p,x), fma(-alpha,Ap,r)).
+template <int VEC>
+__global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                           const double* __restrict__ p,
+                                                           const double* __restrict__ Ap, double* __restrict__ x,
+                                                           double* __restrict__ r, double* __restrict__ partials) {
+    __shared__ double scratch[8];
+    if (sc->converged) return;
+    const double alpha = sc->alpha, nalpha = -alpha;
+    constexpr int UNROLL = 4;
+    const long long tile = 256LL * VEC * UNROLL;
+    double acc = 0.0;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        if (VEC == 2) {
+            double2 pv[UNROLL], av[UNROLL], xv[UNROLL], rv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    pv[u] = __ldcs(reinterpret_cast<const double2*>(p + i));
+                    av[u] = __ldcs(reinterpret_cast<const double2*>(Ap + i));
+                    xv[u] = __ldcs(reinterpret_cast<const double2*>(x + i));
+                    rv[u] = __ldcs(reinterpret_cast<const double2*>(r + i));
+                } else if (i < n) {
+                    pv[u] = make_double2(p[i], 0.0); av[u] = make_double2(Ap[i], 0.0);
+                    xv[u] = make_double2(x[i], 0.0); rv[u] = make_double2(r[i], 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i < n) {
+                    xv[u].x = fma(alpha, pv[u].x, xv[u].x);
+                    rv[u].x = fma(nalpha, av[u].x, rv[u].x);
+                    acc = fma(rv[u].x, rv[u].x, acc);
+                    if (i + 1 < n) {
+                        xv[u].y = fma(alpha, pv[u].y, xv[u].y);
+                        rv[u].y = fma(nalpha, av[u].y, rv[u].y);
+                        acc = fma(rv[u].y, rv[u].y, acc);
+                        *reinterpret_cast<double2*>(x + i) = xv[u];
+                        *reinterpret_cast<double2*>(r + i) = rv[u];
+                    } else {
+                        x[i] = xv[u].x;
+                        r[i] = rv[u].x;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + (long long)u * 256 + threadIdx.x;
+                if (i < n) {
+                    const double xn = fma(alpha, p[i], x[i]);
+                    const double rn = fma(nalpha, Ap[i], r[i]);
+                    x[i] = xn;
+                    r[i] = rn;
+                    acc = fma(rn, rn, acc);
+                }
+            }
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// K3: p = r + beta p   (reference update_p_kernel, cg_solver.cu:91-96: fma(beta,p,r))
+template <int VEC>
+__global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                          const double* __restrict__ r, double* __restrict__ p) {
+    if (sc->converged) return;
+    const double beta = sc->beta;
+    constexpr int UNROLL = 4;
+    const long long tile = 256LL * VEC * UNROLL;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        if (VEC == 2) {
+            double2 pv[UNROLL], rv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    pv[u] = __ldcs(reinterpret_cast<const double2*>(p + i));
+                    rv[u] = __ldcs(reinterpret_cast<const double2*>(r + i));
+                } else if (i < n) {
+                    pv[u] = make_double2(p[i], 0.0);
+                    rv[u] = make_double2(r[i], 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    pv[u].x = fma(beta, pv[u].x, rv[u].x);
+                    pv[u].y = fma(beta, pv[u].y, rv[u].y);
+                    *reinterpret_cast<double2*>(p + i) = pv[u];
+                } else if (i < n) {
+                    p[i] = fma(beta, pv[u].x, rv[u].x);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + (long long)u * 256 + threadIdx.x;
+                if (i < n) p[i] = fma(beta, p[i], r[i]);
+            }
+        }
+    }
+}
+
+// Generic pieces for operators without a fused entry point (any SpmvOperator with run_device):
+// partial dot, r = b - Ap with p = r and r.r
+__global__ void __launch_bounds__(256) dot_partials_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                           const double* __restrict__ x, const double* __restrict__ y,
+                                                           double* __restrict__ partials) {
+    __shared__ double scratch[8];
+    if (sc != nullptr && sc->converged) return;
+    double acc = 0.0;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) acc = fma(x[i], y[i], acc);
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) residual_init_kernel(long long n, const double* __restrict__ b,
+                                                            const double* __restrict__ Ap, double* __restrict__ r,
+                                                            double* __restrict__ p, double* __restrict__ partials) {
+    __shared__ double scratch[8];
+    double acc = 0.0;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) {
+                const double rv = b[i] - Ap[i];
+                r[i] = rv;
+                p[i] = rv;
+                acc = fma(rv, rv, acc);
+            }
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// checksum partials: sum x and sum x^2 (fixed order); replaces the host loops at
+// cg_solver.cu:658-665 for vectors that never leave the device at 20k x 20k
+__global__ void __launch_bounds__(256) checksum_partials_kernel(long long n, const double* __restrict__ x,
+                                                                double* __restrict__ psum, double* __restrict__ psq) {
+    __shared__ double scratch[8];
+    double s = 0.0, q = 0.0;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) { const double v = x[i]; s += v; q = fma(v, v, q); }
+        }
+    }
+    s = block_sum(s, scratch);
+    __syncthreads();
+    q = block_sum(q, scratch);
+    if (threadIdx.x == 0) { psum[blockIdx.x] = s; psq[blockIdx.x] = q; }
+}
+
+// Halo push: the first / last `halo` elements of the local vector go straight into the
+// neighbours' landing buffers over NVLink (peer stores), followed by a release-store of the epoch
+// into the neighbour's flag.  Replaces exchange_halo_mpi (cg_solver_mgpu_partitioned.cu:173-231:
+// D2H, MPI_Isend/Irecv, H2D, two stream syncs).  gridDim.x = 2 * ctas_per_dir.
+struct HaloPushArgs {
+    const double* v_local;
+    long long n_local;
+    int halo;
+    double* dst_prev;  // rank-1's halo_next landing buffer (NULL if rank == 0)
+    double* dst_next;  // rank+1's halo_prev landing buffer (NULL if last rank)
+    uint32_t* flag_prev;  // rank-1's halo_flag_next
+    uint32_t* flag_next;  // rank+1's halo_flag_prev
+    uint32_t epoch;
+    uint32_t* push_count;  // my_xchg->push_count
+    const CGScalars* sc;
+};
+
+__global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
+    if (a.sc != nullptr && a.sc->converged) return;
+    const int per_dir = gridDim.x / 2;
+    const int dir = blockIdx.x / per_dir, blk = blockIdx.x % per_dir;
+    double* dst = dir == 0 ? a.dst_prev : a.dst_next;
+    if (dst == nullptr) return;
+    const double* src = dir == 0 ? a.v_local : a.v_local + (a.n_local - a.halo);
+    for (int i = blk * 256 + threadIdx.x; i < a.halo; i += per_dir * 256) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(&a.push_count[dir], 1u) + 1u;
+        if (done == (uint32_t)per_dir) {
+            a.push_count[dir] = 0;
+            __threadfence_system();
+            st_release_sys(dir == 0 ? a.flag_prev : a.flag_next, a.epoch);
+        }
+    }
+}
+
+}  // namespace b200

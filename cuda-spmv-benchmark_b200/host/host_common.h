@@ -1,0 +1,84 @@
+// host_common.h -- shared declarations of the host layer (C++ above the kernel C ABI).
+// The host layer mirrors the reference's operator / solver / io / bench interface
+// (include/b200/api.h) and talks to the GPU only through include/b200_kernels.h and the CUDA
+// runtime API (allocation, copies, streams, events).  It contains no arithmetic on vectors or
+// matrices: there is no CPU fallback anywhere in the product path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/b200/api.h"
+#include "../../include/b200_kernels.h"
+
+// CUDA failure inside the library: report and return an error code to the caller.  (The
+// reference's CUDA_CHECK calls exit(); a shared library that is also loaded from Python must not
+// take the process down, so the CLIs exit on a non-zero return instead.)
+#define B200_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            fprintf(stderr, "[b200] CUDA error: %s (%s:%d)\n", cudaGetErrorString(e_), __FILE__, \
+                    __LINE__);                                                                   \
+            return 2;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+#define B200_K(call)                                                                             \
+    do {                                                                                         \
+        int rc_ = (call);                                                                        \
+        if (rc_ != 0) {                                                                          \
+            fprintf(stderr, "[b200] kernel ABI error %d: %s (%s:%d)\n", rc_, b200_last_error(),  \
+                    __FILE__, __LINE__);                                                         \
+            return rc_;                                                                          \
+        }                                                                                        \
+    } while (0)
+
+namespace b200host {
+
+// Is `mat` the synthetic stencil of the B200 extension (entries == NULL, grid_size > 0)?
+inline bool is_synthetic(const MatrixData* m) { return m && m->entries == nullptr && m->grid_size > 0; }
+
+// Device-resident matrix slice of one operator (or one band of the multi-GPU solver).
+struct DeviceBand {
+    int* d_row_ptr = nullptr;
+    int* d_col_idx = nullptr;
+    double* d_values = nullptr;
+    long long values_len = 0;
+    long long row_offset = 0;
+    long long n_local = 0;
+    long long nnz_local = 0;
+    int grid = -1;
+    int layout = 0;
+    void release();
+    void describe(b200_band* out) const;
+};
+
+// Builds the device arrays of rows [off, off+nl): from the host CSR in csr_mat (uploaded slice,
+// row_ptr rebased, global columns) or generated on the device for the synthetic stencil.
+int upload_band_csr(const MatrixData* mat, long long off, long long nl, DeviceBand* out, cudaStream_t s);
+int upload_band_ell(const MatrixData* mat, long long off, long long nl, DeviceBand* out, cudaStream_t s);
+
+// operator side-table: the band behind a stencil-type operator (for the fused CG path)
+const DeviceBand* operator_band(const SpmvOperator* op);
+
+// verbose printing switch shared by the solvers
+extern int g_quiet;
+
+}  // namespace b200host
+
+extern "C" {
+// ---- extensions exported next to the reference API (declared here, documented in INTEGRATION.md)
+int b200_operator_band(const SpmvOperator* op, b200_band* out);
+int b200_mgpu_init_single_process(int world, const int* devices, int max_grid);
+int b200_mgpu_init_rank(int rank, int world, int device, int max_grid, void* handle_out64);
+int b200_mgpu_connect(const void* handles);
+int b200_mgpu_world(void);
+int b200_mgpu_rank(void);
+void b200_mgpu_finalize(void);
+MatrixData b200_synthetic_stencil(int grid_size);
+int b200_set_tuning(int variant, int rows_per_item);
+void b200_get_tuning(int* variant, int* rows_per_item);
+}

@@ -1,0 +1,407 @@
+// matrix_io.cpp -- Matrix Market reader / stencil writer and the COO->CSR / CSR->ELLPACK
+// builders behind the reference's io.h / spmv_csr.h / spmv_ellpack.h names.
+//
+// Structure results are bit-identical to the reference (tests/test_structure_parity.py pins
+// them against the reference's own host code and the golden fixtures):
+//   write_matrix_market_stencil5  reference src/io/io.cu:322-399 (byte-identical file)
+//   load_matrix_market / read_matrix_general  reference src/io/io.cu:73-171
+//   build_csr_struct              reference src/spmv/spmv_cusparse_csr.cu:62-170
+// The implementation is new: block-buffered text I/O instead of fprintf/fscanf per entry, and a
+// reader that reports failures through its return code.
+#include <errno.h>
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "host_common.h"
+
+CSRMatrix csr_mat = {0, 0, 0, nullptr, nullptr, nullptr};
+ELLPACKMatrix ellpack_matrix = {0, 0, 0, 0, nullptr, 0, nullptr};
+
+namespace b200host {
+int g_quiet = 0;
+}
+using namespace b200host;
+
+// ------------------------------------------------------------------------------------------------
+// reader
+// ------------------------------------------------------------------------------------------------
+extern "C" int read_matrix_type(const char* filename) {
+    FILE* f = fopen(filename, "r");
+    if (!f) {
+        fprintf(stderr, "Error opening file\n");
+        return -1;
+    }
+    int type = -1;
+    char line[MAX_LINE_LENGTH];
+    // only the leading '%' lines can carry the qualifier (reference io.cu:43-57)
+    while (fgets(line, sizeof line, f) != nullptr && line[0] == '%') {
+        if (strstr(line, "general")) { type = 1; break; }
+        if (strstr(line, "symmetric")) { type = 2; break; }
+    }
+    if (type < 0) fprintf(stderr, "Error opening file\n");
+    fclose(f);
+    return type;
+}
+
+namespace {
+
+struct Header {
+    int rows = 0, cols = 0, nnz = 0, grid = -1;
+};
+
+// Header scan shared by both readers: '%' lines are comments, one of which may carry
+// "% STENCIL_GRID_SIZE n" (io.cu:130-132); the first other line is "rows cols nnz".
+bool read_header(FILE* f, Header* h) {
+    char line[MAX_LINE_LENGTH];
+    while (fgets(line, sizeof line, f) != nullptr) {
+        if (line[0] != '%') return sscanf(line, "%d %d %d", &h->rows, &h->cols, &h->nnz) == 3;
+        if (strstr(line, "STENCIL_GRID_SIZE")) sscanf(line, "%% STENCIL_GRID_SIZE %d", &h->grid);
+    }
+    return false;
+}
+
+// Tokenising entry reader over a large block buffer; accepts exactly what "%d %d %le" accepts
+// (white-space separated, entries may span lines) and converts values with strtod, i.e. the same
+// correctly-rounded conversion fscanf performs.
+class EntryScanner {
+  public:
+    explicit EntryScanner(FILE* f) : f_(f), buf_(1 << 22) {}
+    bool next(int* row, int* col, double* val) {
+        char tok[128];
+        if (!token(tok, sizeof tok) || !parse_int(tok, row)) return false;
+        if (!token(tok, sizeof tok) || !parse_int(tok, col)) return false;
+        if (!token(tok, sizeof tok)) return false;
+        char* end = nullptr;
+        *val = strtod(tok, &end);
+        return end != tok;
+    }
+
+  private:
+    int getc_() {
+        if (pos_ == len_) {
+            len_ = fread(buf_.data(), 1, buf_.size(), f_);
+            pos_ = 0;
+            if (len_ == 0) return EOF;
+        }
+        return (unsigned char)buf_[pos_++];
+    }
+    bool token(char* out, size_t cap) {
+        int c;
+        do { c = getc_(); } while (c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f');
+        if (c == EOF) return false;
+        size_t n = 0;
+        while (c != EOF && !(c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\v' || c == '\f')) {
+            if (n + 1 < cap) out[n++] = (char)c;
+            c = getc_();
+        }
+        out[n] = 0;
+        return n > 0;
+    }
+    static bool parse_int(const char* t, int* v) {
+        char* end = nullptr;
+        errno = 0;
+        long x = strtol(t, &end, 10);
+        if (end == t) return false;
+        *v = (int)x;
+        return true;
+    }
+    FILE* f_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+};
+
+int read_general_impl(MatrixData* mat, const char* filename) {
+    FILE* f = fopen(filename, "r");
+    if (!f) {
+        fprintf(stderr, "Error opening file\n");
+        return 1;
+    }
+    Header h;
+    if (!read_header(f, &h) || h.nnz < 0) {
+        fprintf(stderr, "Error reading matrix size line\n");
+        fclose(f);
+        return 2;
+    }
+    Entry* e = (Entry*)malloc((size_t)(h.nnz > 0 ? h.nnz : 1) * sizeof(Entry));
+    if (!e) {
+        fprintf(stderr, "Allocation failed at line %d\n", __LINE__);
+        fclose(f);
+        return 3;
+    }
+    EntryScanner sc(f);
+    for (int i = 0; i < h.nnz; i++) {
+        if (!sc.next(&e[i].row, &e[i].col, &e[i].value)) {
+            fprintf(stderr, "Error reading matrix entry %d (expected 3 items)\n", i);
+            free(e);
+            fclose(f);
+            mat->entries = nullptr;
+            mat->nnz = 0;
+            return 4;
+        }
+        e[i].row -= 1;  // Matrix Market is 1-based
+        e[i].col -= 1;
+    }
+    fclose(f);
+    mat->entries = e;
+    mat->rows = h.rows; mat->cols = h.cols; mat->nnz = h.nnz; mat->grid_size = h.grid;
+    return 0;
+}
+
+// Symmetric files store one triangle: every off-diagonal entry (i,j) also stands for (j,i).
+// (The reference's symmetric path, io.cu:189-310, builds private CSR arrays and never fills `mat`;
+// SURVEY.md lists it as a bug.  Here the expanded COO list is returned in file order, each mirrored
+// entry directly after its original.)
+int read_symmetric_impl(MatrixData* mat, const char* filename, int* nnz_general) {
+    FILE* f = fopen(filename, "r");
+    if (!f) {
+        fprintf(stderr, "Error opening file\n");
+        return 1;
+    }
+    Header h;
+    if (!read_header(f, &h) || h.nnz < 0) { fclose(f); return 2; }
+    std::vector<Entry> out;
+    out.reserve((size_t)h.nnz * 2);
+    EntryScanner sc(f);
+    for (int i = 0; i < h.nnz; i++) {
+        Entry e;
+        if (!sc.next(&e.row, &e.col, &e.value)) { fclose(f); return 4; }
+        e.row -= 1; e.col -= 1;
+        out.push_back(e);
+        if (e.row != e.col) { Entry m = {e.col, e.row, e.value}; out.push_back(m); }
+    }
+    fclose(f);
+    if (out.size() > 2147483647u) return 5;
+    Entry* arr = (Entry*)malloc((out.empty() ? 1 : out.size()) * sizeof(Entry));
+    if (!arr) return 3;
+    memcpy(arr, out.data(), out.size() * sizeof(Entry));
+    mat->entries = arr;
+    mat->rows = h.rows; mat->cols = h.cols; mat->nnz = (int)out.size(); mat->grid_size = h.grid;
+    if (nnz_general) *nnz_general = (int)out.size();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" void read_matrix_general(MatrixData* mat, const char* filename, int* rows, int* cols, int* nnz,
+                                    int** csr_rowptr, int** csr_colind, double** csr_val) {
+    (void)csr_rowptr; (void)csr_colind; (void)csr_val;  // unused in the reference as well
+    if (read_general_impl(mat, filename) == 0) {
+        if (rows) *rows = mat->rows;
+        if (cols) *cols = mat->cols;
+        if (nnz) *nnz = mat->nnz;
+    }
+}
+
+extern "C" void read_matrix_symtogen(MatrixData* mat, const char* filename, int* rows, int* cols, int* nnz,
+                                     int** csr_rowptr, int** csr_colind, double** csr_val, int* nnz_general) {
+    (void)csr_rowptr; (void)csr_colind; (void)csr_val;
+    if (read_symmetric_impl(mat, filename, nnz_general) == 0) {
+        if (rows) *rows = mat->rows;
+        if (cols) *cols = mat->cols;
+        if (nnz) *nnz = mat->nnz;
+    }
+}
+
+extern "C" int load_matrix_market(const char* filename, MatrixData* mat) {
+    if (!g_quiet) printf("Loading matrix: %s\n", filename);
+    if (!mat) return 1;
+    mat->entries = nullptr; mat->rows = mat->cols = mat->nnz = 0; mat->grid_size = -1;
+    const int type = read_matrix_type(filename);
+    if (type == 2) return read_symmetric_impl(mat, filename, nullptr);
+    return read_general_impl(mat, filename);  // type 1, or unknown header: try the general layout
+}
+
+// ------------------------------------------------------------------------------------------------
+// stencil writer: identical bytes to the reference file, written through a block buffer
+// ------------------------------------------------------------------------------------------------
+namespace {
+class TextSink {
+  public:
+    explicit TextSink(FILE* f) : f_(f) { buf_.reserve(1 << 22); }
+    ~TextSink() { flush(); }
+    void line(int a, int b, const char* tail) {
+        char tmp[48];
+        int n = snprintf(tmp, sizeof tmp, "%d %d %s\n", a, b, tail);
+        buf_.append(tmp, (size_t)n);
+        if (buf_.size() > (1u << 22) - 64) flush();
+    }
+    void flush() {
+        if (!buf_.empty()) fwrite(buf_.data(), 1, buf_.size(), f_);
+        buf_.clear();
+    }
+
+  private:
+    FILE* f_;
+    std::string buf_;
+};
+}  // namespace
+
+extern "C" int write_matrix_market_stencil5(int n, const char* filename) {
+    if (n < 1) return 1;
+    const long long N = (long long)n * n, nnz = 5LL * n * n - 4LL * n;
+    if (nnz > 2147483647LL) {
+        fprintf(stderr, "write_matrix_market_stencil5: %lld non-zeros do not fit the format's int fields\n", nnz);
+        return 1;
+    }
+    FILE* f = fopen(filename, "w");
+    if (!f) {
+        perror("fopen");
+        return 1;
+    }
+    fprintf(f, "%%%%MatrixMarket matrix coordinate real general\n");
+    fprintf(f, "%% STENCIL_GRID_SIZE %d\n", n);
+    fprintf(f, "%d %d %d\n", (int)N, (int)N, (int)nnz);
+    {
+        TextSink out(f);
+        for (int gi = 0; gi < n; gi++) {
+            for (int gj = 0; gj < n; gj++) {
+                const int id = gi * n + gj + 1;
+                out.line(id, id, "5.0");                      // centre
+                if (gj > 0) out.line(id, id - 1, "-1.0");      // left
+                if (gj < n - 1) out.line(id, id + 1, "-1.0");  // right
+                if (gi > 0) out.line(id, id - n, "-1.0");      // top
+                if (gi < n - 1) out.line(id, id + n, "-1.0");  // bottom
+            }
+        }
+    }
+    fclose(f);
+    if (!g_quiet) printf("Matrix generated: %s (%dx%d, %d nnz)\n", filename, (int)N, (int)N, (int)nnz);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// COO -> CSR
+// ------------------------------------------------------------------------------------------------
+// Result: rows in ascending order; inside a row ascending column, equal columns in file order
+// (= counting sort by row that keeps file order, then a stable per-row sort by column).
+int build_csr_struct(struct MatrixData* mat) {
+    if (!mat) return EXIT_FAILURE;
+    if (csr_mat.row_ptr != nullptr && csr_mat.nb_rows == mat->rows && csr_mat.nb_nonzeros == mat->nnz) {
+        if (!g_quiet) printf("CSR structure already built, reusing (%dx%d, %d nnz)\n", mat->rows, mat->cols, mat->nnz);
+        return EXIT_SUCCESS;
+    }
+    if (is_synthetic(mat)) {
+        // closed form of generator -> reader -> sort; only for sizes a host array is sensible for
+        const long long n = mat->grid_size;
+        if ((long long)mat->rows != n * n) return EXIT_FAILURE;
+        int* rp = (int*)malloc(((size_t)mat->rows + 1) * sizeof(int));
+        int* ci = (int*)malloc((size_t)mat->nnz * sizeof(int));
+        double* va = (double*)malloc((size_t)mat->nnz * sizeof(double));
+        if (!rp || !ci || !va) { free(rp); free(ci); free(va); return EXIT_FAILURE; }
+        long long k = 0;
+        for (long long i = 0; i < n; i++)
+            for (long long j = 0; j < n; j++) {
+                const long long r = i * n + j;
+                rp[r] = (int)k;
+                if (i > 0) { ci[k] = (int)(r - n); va[k++] = -1.0; }
+                if (j > 0) { ci[k] = (int)(r - 1); va[k++] = -1.0; }
+                ci[k] = (int)r; va[k++] = 5.0;
+                if (j < n - 1) { ci[k] = (int)(r + 1); va[k++] = -1.0; }
+                if (i < n - 1) { ci[k] = (int)(r + n); va[k++] = -1.0; }
+            }
+        rp[mat->rows] = (int)k;
+        free(csr_mat.row_ptr); free(csr_mat.col_indices); free(csr_mat.values);
+        csr_mat = {mat->rows, mat->cols, mat->nnz, rp, ci, va};
+        return EXIT_SUCCESS;
+    }
+    if (!g_quiet) printf("Building CSR structure (%dx%d, %d nnz)...\n", mat->rows, mat->cols, mat->nnz);
+    const int rows = mat->rows, nnz = mat->nnz;
+    const Entry* E = mat->entries;
+    int* rp = (int*)calloc((size_t)rows + 1, sizeof(int));
+    int* ci = (int*)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(int));
+    double* va = (double*)malloc((size_t)(nnz > 0 ? nnz : 1) * sizeof(double));
+    int* cursor = (int*)malloc((size_t)(rows > 0 ? rows : 1) * sizeof(int));
+    if (!rp || !ci || !va || !cursor) {
+        fprintf(stderr, "[ERROR] allocation failed in build_csr_struct\n");
+        free(rp); free(ci); free(va); free(cursor);
+        return EXIT_FAILURE;
+    }
+    for (int k = 0; k < nnz; k++) rp[E[k].row + 1]++;
+    for (int r = 0; r < rows; r++) { rp[r + 1] += rp[r]; cursor[r] = rp[r]; }
+    for (int k = 0; k < nnz; k++) {
+        const int d = cursor[E[k].row]++;
+        ci[d] = E[k].col;
+        va[d] = E[k].value;
+    }
+    free(cursor);
+    for (int r = 0; r < rows; r++) {
+        const int lo = rp[r], hi = rp[r + 1];
+        for (int a = lo + 1; a < hi; a++) {  // stable insertion: rows hold a handful of entries
+            const int c = ci[a];
+            const double v = va[a];
+            int b = a;
+            while (b > lo && ci[b - 1] > c) { ci[b] = ci[b - 1]; va[b] = va[b - 1]; b--; }
+            ci[b] = c; va[b] = v;
+        }
+    }
+    // the previous arrays are intentionally kept alive by the reference (never freed); here the
+    // old ones are released when a different matrix replaces them
+    free(csr_mat.row_ptr); free(csr_mat.col_indices); free(csr_mat.values);
+    csr_mat = {rows, mat->cols, nnz, rp, ci, va};
+    if (!g_quiet) printf("CSR structure built successfully\n");
+    return EXIT_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR -> ELLPACK  (declared-only in the reference: include/spmv_ellpack.h:50-51, io.h:124-125)
+// width = longest row; row-major; slots beyond a row's length hold index -1 / value 0.0
+// ------------------------------------------------------------------------------------------------
+int build_ellpack_from_csr_struct(const struct CSRMatrix* csr, ELLPACKMatrix* ell, int* max_width) {
+    if (!csr || !ell || !csr->row_ptr) return EXIT_FAILURE;
+    int w = 0;
+    for (int r = 0; r < csr->nb_rows; r++) {
+        const int len = csr->row_ptr[r + 1] - csr->row_ptr[r];
+        if (len > w) w = len;
+    }
+    if (w > MAX_WIDTH) {
+        fprintf(stderr, "[ERROR] ELLPACK width %d exceeds MAX_WIDTH %d\n", w, MAX_WIDTH);
+        return EXIT_FAILURE;
+    }
+    const size_t slots = (size_t)csr->nb_rows * (size_t)(w > 0 ? w : 1);
+    int* idx = (int*)malloc(slots * sizeof(int));
+    double* val = (double*)malloc(slots * sizeof(double));
+    if (!idx || !val) { free(idx); free(val); return EXIT_FAILURE; }
+    for (int r = 0; r < csr->nb_rows; r++) {
+        const int s = csr->row_ptr[r], len = csr->row_ptr[r + 1] - s;
+        int* ir = idx + (size_t)r * w;
+        double* vr = val + (size_t)r * w;
+        for (int k = 0; k < len; k++) { ir[k] = csr->col_indices[s + k]; vr[k] = csr->values[s + k]; }
+        for (int k = len; k < w; k++) { ir[k] = -1; vr[k] = 0.0; }
+    }
+    ell->nb_rows = csr->nb_rows; ell->nb_cols = csr->nb_cols; ell->ell_width = w;
+    ell->grid_size = -1; ell->indices = idx; ell->nb_nonzeros = csr->nb_nonzeros; ell->values = val;
+    if (max_width) *max_width = w;
+    return EXIT_SUCCESS;
+}
+
+extern "C" void convert_csr_to_ellpack(const struct CSRMatrix* csr, struct ELLPACKMatrix* ell, int* max_width) {
+    build_ellpack_from_csr_struct(csr, ell, max_width);
+}
+
+extern "C" int build_ellpack_from_csr_local(CSRMatrix* csr) {
+    free(ellpack_matrix.indices); free(ellpack_matrix.values);
+    ellpack_matrix.indices = nullptr; ellpack_matrix.values = nullptr;
+    int w = 0;
+    return build_ellpack_from_csr_struct(csr, &ellpack_matrix, &w);
+}
+
+extern "C" int ensure_ellpack_structure_built(MatrixData* mat) {
+    if (build_csr_struct(mat) != EXIT_SUCCESS) return EXIT_FAILURE;
+    if (ellpack_matrix.indices != nullptr && ellpack_matrix.nb_rows == mat->rows &&
+        ellpack_matrix.nb_nonzeros == mat->nnz) {
+        ellpack_matrix.grid_size = mat->grid_size;
+        return EXIT_SUCCESS;
+    }
+    if (build_ellpack_from_csr_local(&csr_mat) != EXIT_SUCCESS) return EXIT_FAILURE;
+    ellpack_matrix.grid_size = mat->grid_size;
+    return EXIT_SUCCESS;
+}
+
+extern "C" MatrixData b200_synthetic_stencil(int n) {
+    MatrixData m;
+    const long long N = (long long)n * n, nnz = 5LL * n * n - 4LL * n;
+    m.rows = (int)N; m.cols = (int)N; m.nnz = (int)nnz; m.grid_size = n; m.entries = nullptr;
+    return m;
+}

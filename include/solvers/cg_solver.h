@@ -1,0 +1,4 @@
+/* solvers/cg_solver.h -- drop-in shim: same include name as the reference's include/solvers/cg_solver.h; the
+ * declarations live in b200/api.h. */
+#pragma once
+#include "../b200/api.h"

@@ -308,7 +308,9 @@ class RefHost:
     def __init__(self):
         if not os.path.exists(REF_HOST_PATH):
             raise FileNotFoundError(REF_HOST_PATH)
-        self.L = C.CDLL(REF_HOST_PATH)
+        # DEEPBIND: the reference library must bind ITS OWN csr_mat / load_matrix_market / ... even if
+        # the product library (same symbol names by design) is loaded in this process
+        self.L = C.CDLL(REF_HOST_PATH, mode=os.RTLD_LOCAL | os.RTLD_DEEPBIND)
         self.L.write_matrix_market_stencil5.argtypes = [C.c_int, C.c_char_p]
         self.L.load_matrix_market.argtypes = [C.c_char_p, C.POINTER(Matrix)]
         self.build = getattr(self.L, "_Z16build_csr_structP10MatrixData")

@@ -1,0 +1,162 @@
+"""CPU: the product's host layer (libspmv_b200.so) -- ABI exports, Matrix Market I/O, COO->CSR,
+CSR->ELLPACK, bench statistics, exporters -- against the oracle and the golden fixtures.
+No compute entry point is called here (no GPU in this tier)."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+META = json.load(open(os.path.join(GOLDEN, "structure_meta.json")))
+
+
+def test_library_exports_every_declared_symbol(B):
+    L = B.load()
+    missing = [s for s in B.C_SYMBOLS if not hasattr(L, s)]
+    missing += [k for k, v in B.CXX_SYMBOLS.items() if not hasattr(L, v)]
+    assert not missing, missing
+    # every function declared in include/b200_kernels.h is bound
+    hdr = open(os.path.join(ROOT, "include", "b200_kernels.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared and declared <= set(B.C_SYMBOLS), declared - set(B.C_SYMBOLS)
+    assert L.b200_version().startswith(b"b200-spmv-cg")
+
+
+def test_struct_layouts_match_reference_headers(B):
+    assert C.sizeof(B.Entry) == 16 and C.sizeof(B.MatrixData) == 24
+    assert C.sizeof(B.CGConfig) == 24 and C.sizeof(B.CGStats) == 72 and C.sizeof(B.BenchmarkStats) == 48
+    assert C.sizeof(B.SpmvOperator) == 40 and C.sizeof(B.CGStatsMultiGPU) == 144
+    L = B.load()
+    assert L.b200_cg_scalars_bytes() >= 64 and L.b200_xchg_bytes() % 8 == 0
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16])
+def test_writer_reader_builder_vs_golden(B, orc, n, tmp_path):
+    L = B.load()
+    p = str(tmp_path / "s.mtx")
+    assert L.write_matrix_market_stencil5(n, p.encode()) == 0
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == META["files"]["stencil_%d" % n]
+    assert L.read_matrix_type(p.encode()) == 1
+    hm = B.HostMatrix.from_mtx(p)
+    assert (hm.md.rows, hm.md.cols, hm.md.nnz, hm.md.grid_size) == (n * n, n * n, 5 * n * n - 4 * n, n)
+    ent = hm.entries_array()
+    assert ent.tobytes() == orc.stencil5_entries(n).tobytes()
+    L.csr_mat  # noqa: B018
+    B.csr_mat().row_ptr = None  # force a rebuild (re-use guard keys on rows/nnz only)
+    assert L.build_csr_struct(hm.ptr()) == 0
+    rp, ci, va = B.host_csr_arrays()
+    g = np.load(os.path.join(GOLDEN, "structure.npz"))
+    assert np.array_equal(rp, g["n%d_row_ptr" % n]) and np.array_equal(ci, g["n%d_col" % n])
+    assert np.array_equal(va, g["n%d_val" % n])
+
+
+def test_builder_random_duplicates_and_ellpack(B, orc, tmp_path):
+    L = B.load()
+    rng = np.random.default_rng(5)
+    rows, nnz = 50, 700
+    ent = np.zeros(nnz, dtype=B.ENTRY_DTYPE)
+    ent["row"], ent["col"] = rng.integers(0, rows, nnz), rng.integers(0, rows, nnz)
+    ent["value"] = rng.uniform(-1, 1, nnz)
+    hm = B.HostMatrix.from_entries(rows, rows, ent)
+    B.csr_mat().row_ptr = None
+    assert L.build_csr_struct(hm.ptr()) == 0
+    rp, ci, va = B.host_csr_arrays()
+    orp, oci, ova = orc.build_csr(rows, rows, ent)
+    assert np.array_equal(rp, orp) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+    B.ellpack_matrix().indices = None
+    assert L.ensure_ellpack_structure_built(hm.ptr()) == 0
+    e = B.ellpack_matrix()
+    w, oidx, oval = orc.build_ellpack(orp, oci, ova, rows, rows)
+    assert e.ell_width == w and e.nb_rows == rows and e.nb_nonzeros == nnz
+    idx = np.ctypeslib.as_array(e.indices, shape=(rows * w,))
+    val = np.ctypeslib.as_array(e.values, shape=(rows * w,))
+    assert np.array_equal(idx, oidx) and np.array_equal(val, oval)
+
+
+def test_synthetic_matrix_host_csr_equals_oracle(B, orc):
+    L = B.load()
+    hs = B.HostMatrix.synthetic_stencil(12)
+    assert hs.md.rows == 144 and hs.md.nnz == 5 * 144 - 48 and not hs.md.entries
+    B.csr_mat().row_ptr = None
+    assert L.build_csr_struct(hs.ptr()) == 0
+    rp, ci, va = B.host_csr_arrays()
+    rp64, oci, ova = orc.stencil5_csr_direct(12)
+    assert np.array_equal(rp, rp64) and np.array_equal(ci, oci) and np.array_equal(va, ova)
+    for r in (0, 1, 11, 12, 13, 77, 143, 144):
+        assert L.b200_stencil5_nnz_before(r, 12) == rp64[r]
+
+
+def test_symmetric_reader_expands(B, tmp_path):
+    p = str(tmp_path / "sym.mtx")
+    open(p, "w").write("%%MatrixMarket matrix coordinate real symmetric\n3 3 4\n1 1 2.0\n2 1 -1.0\n2 2 2.0\n3 2 -1.5\n")
+    assert B.load().read_matrix_type(p.encode()) == 2
+    hm = B.HostMatrix.from_mtx(p)
+    e = hm.entries_array()
+    assert hm.md.nnz == 6
+    assert list(zip(e["row"], e["col"], e["value"])) == [(0, 0, 2.0), (1, 0, -1.0), (0, 1, -1.0), (1, 1, 2.0),
+                                                          (2, 1, -1.5), (1, 2, -1.5)]
+
+
+def test_reader_errors_are_reported(B, tmp_path):
+    L = B.load()
+    md = B.MatrixData()
+    assert L.load_matrix_market(str(tmp_path / "missing.mtx").encode(), C.byref(md)) != 0
+    p = str(tmp_path / "short.mtx")
+    open(p, "w").write("%%MatrixMarket matrix coordinate real general\n2 2 3\n1 1 1.0\n")
+    assert L.load_matrix_market(p.encode(), C.byref(md)) != 0 and not md.entries
+    assert L.get_operator(b"does-not-exist") in (None,) or not L.get_operator(b"does-not-exist")
+    for name in (b"cusparse-csr", b"csr", b"stencil5-csr", b"stencil5", b"ellpack", b"stencil5-ellpack",
+                 b"stencil5-halo-mgpu"):
+        assert L.get_operator(name)
+
+
+def test_benchmark_with_stats_rule(B, orc):
+    L = B.load()
+    times = [10.0, 10.2, 9.9, 10.1, 30.0, 10.0, 9.8, 10.3, 10.1, 10.0]
+    it = iter(times)
+
+    @B.RUN_TIMED_FN
+    def fake_run(x, y, ms):
+        ms[0] = next(it)
+        return 0
+
+    st = B.BenchmarkStats()
+    assert L.benchmark_with_stats(fake_run, None, None, len(times), C.byref(st)) == 0
+    rc, ost = orc.bench_stats(times)
+    got = B.stats_dict(st)
+    for k, v in ost.items():
+        assert got[k] == pytest.approx(v, rel=1e-15), k
+    it = iter([1.0, 2.0])
+    assert L.benchmark_with_stats(fake_run, None, None, 2, C.byref(st)) == -1
+
+
+def test_cg_json_export_schema(B, tmp_path):
+    """Key set / nesting / order of export_cg_json (reference cg_metrics.cu:20-81)."""
+    L = B.load()
+    hs = B.HostMatrix.synthetic_stencil(4)
+    bs = B.BenchmarkStats(1.5, 1.6, 0.1, 1.4, 1.9, 9, 1)
+    cs = B.CGStats(14, 1e-3, 1.5, 0.7, 0.5, 0.1, 1, 3.0, 2.0)
+    p = str(tmp_path / "cg.json")
+    L.export_cg_json(p.encode(), b"stencil5-csr", hs.ptr(), C.byref(bs), C.byref(cs))
+    d = json.load(open(p))
+    assert list(d.keys()) == ["timestamp", "solver", "mode", "matrix", "convergence", "timing", "statistics",
+                              "performance", "validation"]
+    assert d["solver"] == "CG" and d["convergence"] == {"converged": True, "iterations": 14, "residual_norm": 1e-3}
+    assert list(d["timing"].keys()) == ["median_ms", "mean_ms", "min_ms", "max_ms", "std_dev_ms", "spmv_ms",
+                                        "blas1_ms", "reductions_ms"]
+    assert d["matrix"] == {"rows": 16, "cols": 16, "nnz": 64, "grid_size": 4}
+    ms = B.CGStatsMultiGPU()
+    ms.iterations, ms.time_spmv_ms, ms.converged = 14, 0.5, 1
+    p2 = str(tmp_path / "mg.json")
+    L.export_cg_mgpu_json(p2.encode(), b"partitioned-halo", hs.ptr(), C.byref(bs), C.byref(ms), 8)
+    d2 = json.load(open(p2))
+    assert d2["num_gpus"] == 8 and d2["solver"] == "CG Multi-GPU" and "allgather_ms" in d2["timing"]
+    p3 = str(tmp_path / "cg.csv")
+    L.export_cg_csv(p3.encode(), b"stencil5-csr", hs.ptr(), C.byref(bs), C.byref(cs), True)
+    lines = open(p3).read().splitlines()
+    assert lines[0].startswith("mode,rows,cols,nnz,grid_size,converged,iterations") and lines[1].startswith("stencil5-csr,16,16,64,4,1,14,")

@@ -1,0 +1,220 @@
+"""CPU: pins the oracle against (1) golden fixtures made from the reference's own host code,
+(2) the known answers the reference documents, (3) the reference's GPU CLI outputs captured on a
+B200 (tests/golden/ref_gpu.json, produced by oracle/run_ref_gpu.sh)."""
+import hashlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+META = json.load(open(os.path.join(GOLDEN, "structure_meta.json")))
+NPZ = np.load(os.path.join(GOLDEN, "structure.npz"))
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16])
+def test_generator_reader_csr_match_reference_fixture(orc, n, tmp_path):
+    p = str(tmp_path / "s.mtx")
+    orc.write_mtx_stencil5(n, p)
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == META["files"]["stencil_%d" % n]
+    rows, cols, nnz, grid, ent = orc.load_mtx(p)
+    assert dict(rows=rows, cols=cols, nnz=nnz, grid_size=grid) == META["n%d" % n]
+    assert np.array_equal(ent["row"], NPZ["n%d_entries_row" % n])
+    assert np.array_equal(ent["col"], NPZ["n%d_entries_col" % n])
+    assert np.array_equal(ent["value"], NPZ["n%d_entries_val" % n])
+    gen = orc.stencil5_entries(n)
+    assert gen.tobytes() == ent.tobytes()
+    rp, ci, va = orc.build_csr(rows, cols, ent)
+    assert np.array_equal(rp, NPZ["n%d_row_ptr" % n])
+    assert np.array_equal(ci, NPZ["n%d_col" % n])
+    assert np.array_equal(va, NPZ["n%d_val" % n])
+    rp64, ci2, va2 = orc.stencil5_csr_direct(n)
+    assert np.array_equal(rp64, rp) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+    assert nnz == orc.stencil5_nnz(n)
+
+
+def _bundled(orc, tmp_path):
+    """matrix/example81x81.mtx re-created byte for byte (centre token "-4.0")."""
+    p = str(tmp_path / "example81x81.mtx")
+    orc.write_mtx_stencil5(81, p, "-4.0", "-1.0")
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == META["bundled81"]["sha256"]
+    rows, cols, nnz, grid, ent = orc.load_mtx(p)
+    return rows, cols, nnz, grid, ent
+
+
+def test_bundled_81x81_structure(orc, tmp_path):
+    rows, cols, nnz, grid, ent = _bundled(orc, tmp_path)
+    b = META["bundled81"]
+    assert (rows, cols, nnz, grid) == (b["rows"], b["cols"], b["nnz"], b["grid_size"]) == (6561, 6561, 32481, 81)
+    assert hashlib.sha256(ent.tobytes()).hexdigest() == b["entries_sha256"]
+    rp, ci, va = orc.build_csr(rows, cols, ent)
+    assert hashlib.sha256(rp.tobytes() + ci.tobytes() + va.tobytes()).hexdigest() == b["csr_sha256"]
+
+
+def test_bundled_81x81_spmv_and_cg_kats(orc, tmp_path):
+    """BASELINE.md known answers: SpMV x=1 -> sum -52164 (exact), norm 644.2452948994; CG 40 it."""
+    rows, cols, nnz, grid, ent = _bundled(orc, tmp_path)
+    rp, ci, va = orc.build_csr(rows, cols, ent)
+    y = orc.csr_spmv(rp, ci, va, np.ones(rows))
+    ys = orc.stencil5_spmv(rp, ci, va, np.ones(rows), grid)
+    assert y.sum() == -52164.0 and np.array_equal(y, ys)
+    assert math.isclose(math.sqrt((y * y).sum()), 644.2452948994, rel_tol=1e-12)
+    x, res, hist = orc.cg_device(rp, ci, va, grid, 1, np.ones(rows), np.zeros(rows))
+    assert res["iterations"] == 40 and res["converged"] == 1
+    assert math.isclose(res["solution_sum"], -826.0838884, rel_tol=1e-9)
+    assert math.isclose(res["solution_norm"], 10.20619705, rel_tol=1e-9)
+    assert math.isclose(res["residual_norm"] / res["b_norm"], 9.897e-7, rel_tol=1e-3)
+
+
+def test_reference_gtest_kats(orc):
+    """tests/test_wrapper_basic.cpp:102-128 (3x3, centre -4: sum -60) and the analytic fixtures of
+    tests/helpers/matrix_fixtures.cpp:27-111 (identity 3, diag 15/sqrt55, tridiag 2/sqrt2, upper-tri 21/sqrt153)."""
+    e = orc.stencil5_entries(3, -4.0, -1.0)
+    rp, ci, va = orc.build_csr(9, 9, e)
+    assert orc.csr_spmv(rp, ci, va, np.ones(9)).sum() == -60.0
+    assert orc.stencil5_spmv(rp, ci, va, np.ones(9), 3).sum() == -60.0
+    assert len(e) == 33
+
+    def coo(rows, triples):
+        a = np.zeros(len(triples), dtype=orc.ENTRY_DTYPE)
+        for k, (r, c, v) in enumerate(triples):
+            a[k] = (r, c, v)
+        return orc.build_csr(rows, rows, a)
+
+    y = orc.csr_spmv(*coo(3, [(0, 0, 1.0), (1, 1, 1.0), (2, 2, 1.0)]), np.ones(3))
+    assert y.sum() == 3.0
+    y = orc.csr_spmv(*coo(5, [(i, i, float(i + 1)) for i in range(5)]), np.ones(5))
+    assert y.sum() == 15.0 and math.isclose(np.linalg.norm(y), math.sqrt(55))
+    tri = [(0, 0, 2.0), (0, 1, -1.0), (1, 0, -1.0), (1, 1, 2.0), (1, 2, -1.0), (2, 1, -1.0), (2, 2, 2.0),
+           (2, 3, -1.0), (3, 2, -1.0), (3, 3, 2.0)]
+    y = orc.csr_spmv(*coo(4, tri), np.ones(4))
+    assert y.sum() == 2.0 and math.isclose(np.linalg.norm(y), math.sqrt(2))
+    up = [(0, 0, 1.0), (0, 1, 2.0), (0, 2, 3.0), (1, 1, 4.0), (1, 2, 5.0), (2, 2, 6.0)]
+    y = orc.csr_spmv(*coo(3, up), np.ones(3))
+    assert y.sum() == 21.0 and math.isclose(np.linalg.norm(y), math.sqrt(153))
+
+
+@pytest.mark.parametrize("n,iters,ssum,snorm", [
+    (3, 3, None, None), (81, 18, 6363.123899, 78.876260), (512, 17, 260880.6333, 509.870550)])
+def test_cg_iteration_kats(orc, n, iters, ssum, snorm):
+    """Survey/BASELINE known answers; 512^2 also matches the AmgX README figures (17 it, 2.608806e5, 509.87)."""
+    rp64, ci, va = orc.stencil5_csr_direct(n)
+    x, res, hist = orc.cg_device(rp64.astype(np.int32), ci, va, n, 1, np.ones(n * n), np.zeros(n * n))
+    assert res["iterations"] == iters and res["converged"] == 1
+    if ssum is not None:
+        assert math.isclose(res["solution_sum"], ssum, rel_tol=1e-9)
+        assert math.isclose(res["solution_norm"], snorm, rel_tol=1e-7)
+    # generic-CSR operator gives the same iteration count
+    x2, res2, _ = orc.cg_device(rp64.astype(np.int32), ci, va, n, 0, np.ones(n * n), np.zeros(n * n))
+    assert res2["iterations"] == iters
+
+
+def test_spmv_x1_closed_form(orc):
+    """5/-1 stencil, x = 1: interior y=1, edge 2, corner 3 -> sum = N + 4n (exact)."""
+    for n in (2, 3, 10, 65, 130):
+        rp64, ci, va = orc.stencil5_csr_direct(n)
+        rp = rp64.astype(np.int32)
+        y = orc.stencil5_spmv(rp, ci, va, np.ones(n * n), n)
+        assert y.sum() == n * n + 4 * n
+        assert np.array_equal(y, orc.csr_spmv(rp, ci, va, np.ones(n * n)))
+
+
+def test_interior_offset_and_ellpack(orc):
+    n = 9
+    rp64, ci, va = orc.stencil5_csr_direct(n)
+    for i in range(1, n - 1):
+        for j in range(1, n - 1):
+            assert orc.interior_csr_offset(i * n + j, n) == rp64[i * n + j]
+    w, idx, val = orc.build_ellpack(rp64.astype(np.int32), ci, va, n * n, n * n)
+    assert w == 5 and (idx.reshape(-1, 5)[0] == [0, 1, n, -1, -1]).all()
+    rng = np.random.default_rng(42)
+    x = rng.random(n * n)
+    assert np.array_equal(orc.ell_spmv(w, idx, val, x, n * n, n * n), orc.csr_spmv(rp64.astype(np.int32), ci, va, x))
+
+
+@pytest.mark.parametrize("n,P", [(8, 2), (9, 2), (81, 2), (81, 4), (16, 3)])
+def test_partition_halo_and_band_spmv(orc, n, P):
+    """Band SpMV with halos over P virtual ranks == full SpMV; partition rule of
+    cg_solver_mgpu_partitioned.cu:262-268; halo ranges :697-703."""
+    N = n * n
+    rp64, ci, va = orc.stencil5_csr_direct(n)
+    rp = rp64.astype(np.int32)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(N)
+    y_full = orc.stencil5_spmv(rp, ci, va, x, n)
+    covered = 0
+    for g in range(P):
+        nl, off = orc.partition(N, P, g)
+        assert off == g * (N // P) and (nl == N // P or g == P - 1)
+        covered += nl
+        lrp, lci, lva = orc.local_csr_slice(rp, ci, va, off, nl)
+        assert lrp[0] == 0 and lrp[-1] == len(lva) and np.array_equal(lci, ci[rp[off]:rp[off + nl]])
+        plo, phi, nlo, nhi = orc.halo_ranges(nl, n, g, P)
+        assert (phi - plo == (n if g > 0 else 0)) and (nhi - nlo == (n if g < P - 1 else 0))
+        hp = x[off - n:off] if g > 0 else None
+        hn = x[off + nl:off + nl + n] if g < P - 1 else None
+        y = orc.halo_spmv(lrp, lci, lva, x[off:off + nl], hp, hn, off, N, n)
+        assert np.array_equal(y, y_full[off:off + nl])
+    assert covered == N
+
+
+def test_cg_mgpu_restatement_matches_single(orc):
+    n = 81
+    rp64, ci, va = orc.stencil5_csr_direct(n)
+    rp = rp64.astype(np.int32)
+    b, x0 = np.ones(n * n), np.zeros(n * n)
+    x1, r1, _ = orc.cg_device(rp, ci, va, n, 1, b, x0)
+    for P in (1, 2, 4, 8):
+        xp, rp_ = orc.cg_mgpu(rp, ci, va, n, P, b, x0)
+        assert rp_["iterations"] == r1["iterations"] == 18
+        assert np.linalg.norm(xp - x1) / np.linalg.norm(x1) < 1e-12
+
+
+def test_bench_stats_rule(orc):
+    """benchmark_stats.cu:39-89: 2-sigma filter then mean/sigma/median/min/max."""
+    t = [10.0, 10.2, 9.9, 10.1, 30.0, 10.0, 9.8, 10.3, 10.1, 10.0]
+    rc, st = orc.bench_stats(t)
+    assert rc == 0 and st["outliers_removed"] == 1 and st["valid_runs"] == 9
+    kept = sorted(v for v in t if v != 30.0)
+    assert st["median_ms"] == kept[4] and st["min_ms"] == 9.8 and st["max_ms"] == 10.3
+    assert orc.bench_stats([1.0, 2.0])[0] == -1
+
+
+def test_dot_blocktree_vs_numpy(orc):
+    rng = np.random.default_rng(3)
+    for n in (1, 255, 256, 257, 100000):
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        d = orc.dot_blocktree(x, y)
+        assert math.isclose(d, float(np.dot(x, y)), rel_tol=1e-11, abs_tol=1e-11)
+
+
+REF_GPU = os.path.join(GOLDEN, "ref_gpu.json")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU), reason="reference GPU outputs not captured yet")
+def test_oracle_matches_reference_gpu_outputs(orc, tmp_path):
+    """The reference's own CLIs (oracle/_ref/spmv_bench, cg_solver built from its sources) run on a
+    B200 by oracle/run_ref_gpu.sh: iteration counts must be equal, checksums agree to 1e-12 / 1e-9."""
+    ref = json.load(open(REF_GPU))
+    for case in ref["cases"]:
+        n, center = case["n"], case["center"]
+        rp64, ci, va = orc.stencil5_csr_direct(n, center, -1.0)
+        rp = rp64.astype(np.int32)
+        N = n * n
+        if "spmv" in case:
+            y = orc.stencil5_spmv(rp, ci, va, np.ones(N), n)
+            for opname, s in case["spmv"].items():
+                assert math.isclose(float(y.sum()), s["sum_y"], rel_tol=1e-13, abs_tol=1e-9), (n, opname)
+                assert math.isclose(math.sqrt(float((y * y).sum())), s["norm2_y"], rel_tol=1e-12), (n, opname)
+        if "cg" in case:
+            for opname, c in case["cg"].items():
+                op = 1 if opname.startswith("stencil5") else 0
+                x, res, _ = orc.cg_device(rp, ci, va, n, op, np.ones(N), np.zeros(N))
+                assert res["iterations"] == c["iterations"], (n, opname)
+                assert res["converged"] == int(c["converged"])
+                assert math.isclose(res["residual_norm"], c["residual_norm"], rel_tol=1e-6), (n, opname)
+                assert math.isclose(res["solution_sum"], c["solution_sum"], rel_tol=1e-10), (n, opname)
+                assert math.isclose(res["solution_norm"], c["solution_norm"], rel_tol=1e-10), (n, opname)
