@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: CG time-to-solution on the 20k x 20k 5-point FP64 stencil
+(BASELINE.json: "CG solve ms & SpMV HBM GB/s, 20k^2 5-pt FP64 stencil, 1/2/4/8 B200").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--grid n]
+
+One "step" = one full CG solve (b = 1, x0 = 0, tol 1e-6, the reference CLI's defaults,
+src/main/cg_solver.cu:50-51,124-128) through the reference-facing entry points of
+libspmv_b200.so.  N > 1 runs one process per GPU (torchrun): torch.distributed is only plumbing
+(rendezvous, IPC-handle all-gather, barrier, max over ranks); halos and scalar reductions move
+through the library's own peer-memory kernels.  Strong scaling: the 20k^2 problem is split into
+N row bands.
+
+Printed JSON line (rank 0): see the keys below.  `value` = device-timed solve (inputs resident in
+HBM, the reference's own timing scope, cg_solver.cu:494,640), max over ranks, mean over K steps.
+`e2e` = the same solve through cg_solve_device / cg_solve_mgpu_partitioned with HOST (pinned)
+buffers, wall clock, copies inside.  `roofline` = the fused STENCIL5 SpMV + p.Ap kernel, timed
+with CUDA events on its stream inside the timed steps.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-spmv-benchmark_b200", "python"))
+
+METRIC = "cg_solve_ms_20k_stencil5_fp64"
+TOL, MAX_ITERS = 1e-6, 1000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=20000)
+    ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference has no CPU compute path -- BASELINE.md section 3)
+# ------------------------------------------------------------------------------------------------
+def cpu_cg_sample(grid_full, cpu_grid, repeats=1):
+    """Bounded sample: full CG to convergence on a smaller grid with the OpenMP oracle, scaled to
+    the full workload by rows x iterations (streaming kernels: time/row/iteration is size independent)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import orc
+    threads = orc.num_threads()
+    n = cpu_grid or (6000 if threads >= 16 else 4000 if threads >= 8 else 2500)
+    rp64, ci, va = orc.stencil5_csr_direct(n)
+    rp = rp64.astype(np.int32)
+    b, x0 = np.ones(n * n), np.zeros(n * n)
+    best, iters = None, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        x, res, _ = orc.cg_device(rp, ci, va, n, 1, b, x0, MAX_ITERS, TOL)
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+        iters = res["iterations"]
+    full_iters = 14  # 20k^2; every size >= 10k converges in 14
+    scaled = best * (grid_full * grid_full * full_iters) / (n * n * iters)
+    sample = ("full CG (oracle port of cg_solve_device, CSR stencil operator, OpenMP %d threads) on a %dx%d grid "
+              "(%d rows, %d iterations, %.0f ms), scaled by rows*iterations to %dx%d / %d iterations"
+              % (threads, n, n, n * n, iters, best, grid_full, grid_full, full_iters))
+    return scaled, threads, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, threads, sample = cpu_cg_sample(args.grid, args.cpu_grid)
+        if s >= args.warmup:
+            vals.append(v)
+    val = sum(vals) / len(vals)
+    line = {"metric": METRIC, "value": val, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": val, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (args.grid, args.grid), "grid": args.grid,
+                       "rows": args.grid ** 2, "tol": TOL},
+            "cpu_baseline": {"value": val, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import spmv_b200 as B
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    L = B.load()
+    n = args.grid
+    N = n * n
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        handle = (C.c_ubyte * 64)()
+        rc = L.b200_mgpu_init_rank(rank, world, local_rank, n, handle)
+        if rc:
+            raise SystemExit("b200_mgpu_init_rank rc=%d" % rc)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        raw = torch.cat(allh).cpu().numpy().tobytes()
+        blob = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        rc = L.b200_mgpu_connect(blob)
+        if rc:
+            raise SystemExit("b200_mgpu_connect rc=%d" % rc)
+        dist.barrier()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    mat = B.HostMatrix.synthetic_stencil(n)
+    nl, off = (N // world, rank * (N // world))
+    if rank == world - 1:
+        nl = N - off
+    # pinned host buffers of the local slice; the solver only touches [off, off+nl) of b and x
+    b_host = torch.ones(nl, dtype=torch.float64).pin_memory()
+    x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
+    b_ptr = b_host.data_ptr() - off * 8
+    x_ptr = x_host.data_ptr() - off * 8
+    cfg = B.cg_config(MAX_ITERS, TOL, 0, 1)  # detailed timers: event records only, no extra syncs
+
+    if world == 1:
+        op = L.get_operator(b"stencil5-csr")
+        if op.contents.init(mat.ptr()) != 0:
+            raise SystemExit("operator init failed")
+        stats = B.CGStats()
+
+        def solve():
+            x_host.zero_()
+            return L.cg_solve_device(op, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
+    else:
+        stats = B.CGStatsMultiGPU()
+
+        def solve():
+            x_host.zero_()
+            return L.cg_solve_mgpu_partitioned(None, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
+
+    for _ in range(args.warmup):
+        barrier()
+        if solve() != 0:
+            raise SystemExit("warm-up solve failed")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.b200_launch_count()
+    dev_ms, wall_ms, k1_ms, k1_cnt, iters = [], [], 0.0, 0, None
+    ph = (C.c_double * 9)()
+    pc = (C.c_int * 9)()
+    barrier()
+    t_block0 = time.perf_counter()
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        rc = solve()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if rc != 0:
+            raise SystemExit("solve failed rc=%d" % rc)
+        d = stats.time_total_ms
+        if dist is not None:  # slowest rank defines the step
+            t = torch.tensor([d, wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d, wall = float(t[0]), float(t[1])
+        dev_ms.append(d)
+        wall_ms.append(wall)
+        L.b200_last_phase_times(ph, pc)
+        k1_ms += ph[1]
+        k1_cnt += pc[1]
+        iters = stats.iterations
+        if not stats.converged:
+            raise SystemExit("CG did not converge")
+    barrier()
+    block_ms = (time.perf_counter() - t_block0) * 1e3
+    launches = L.b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms = sum(dev_ms) / len(dev_ms)
+    e2e_ms = sum(wall_ms) / len(wall_ms)
+    peak, peak_src = measured_peak()
+    rows_local = nl
+    nnz_local = L.b200_stencil5_nnz_before(off + nl, n) - L.b200_stencil5_nnz_before(off, n)
+    k1_bytes = 8.0 * nnz_local + 16.0 * rows_local  # values + p once + Ap   
+    k1_avg_ms = k1_ms / max(k1_cnt, 1)
+    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_cnt else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("stencil5_dot_dram_bytes_per_launch_%d" % n)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "b200",
+        "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (n, n), "grid": n, "rows": N,
+                   "nnz": 5 * N - 4 * n, "tol": TOL, "iterations": iters, "operator": "stencil5-csr",
+                   "partition": "row bands x%d" % world,
+                   "cache": "vectors (3.2 GB each) and matrix (16 GB values) exceed the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 16 * nl, "d2h_bytes_per_step": 8 * nl,
+                "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
+                "host_buffers": "pinned", "block_wall_ms_per_step": block_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "stencil5_kernel<ST_DOT> (SpMV + p.Ap)", "achieved": achieved,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt},
+        "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV+dot launch inside CG"},
+        "cg": {"iterations": iters, "residual_norm": stats.residual_norm, "solution_sum": stats.solution_sum,
+               "solution_norm": stats.solution_norm,
+               "iter_bytes_model": 128.0 * rows_local,
+               "solve_gb_s": (14 * 128.0 + 104.0) * rows_local / (ms * 1e-3) / 1e9},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, sample = cpu_cg_sample(n, args.cpu_grid)
+        line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        L.b200_mgpu_finalize()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_b200(a))

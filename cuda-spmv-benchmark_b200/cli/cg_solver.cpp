@@ -1,0 +1,62 @@
+// cg_solver <file.mtx | --grid=n> [--mode=a[,b]] [--host] [--tol=] [--maxiter=] [--timers] [--json=] [--csv=]
+// reference src/main/cg_solver.cu:23-243: defaults stencil5-csr / device path / tol 1e-6 / 1000 it,
+// b = 1, x0 = 0, 3 warm-up solves, cg_benchmark_with_stats_device(10), "<json>_<mode>.json", CSV appended.
+#include "cli_common.h"
+
+int main(int argc, char** argv) {
+    CliArgs a = parse_cli(argc, argv);
+    if (a.matrix.empty() && a.grid <= 0) {
+        fprintf(stderr, "Usage: %s <matrix.mtx | --grid=n> [--mode=<m1[,m2]>] [--host] [--tol=<t>] [--maxiter=<n>] "
+                        "[--timers] [--json=<file>] [--csv=<file>]\n", argv[0]);
+        return EXIT_FAILURE;
+    }
+    if (a.modes.empty()) a.modes.push_back("stencil5-csr");
+    for (auto& m : a.modes)
+        if (!get_operator(m.c_str())) { fprintf(stderr, "Unknown mode '%s'\n", m.c_str()); return EXIT_FAILURE; }
+    MatrixData mat;
+    if (load_or_generate(a, &mat)) return EXIT_FAILURE;
+    printf("Matrix: %d x %d, %d nonzeros, grid %d\n", mat.rows, mat.cols, mat.nnz, mat.grid_size);
+    std::vector<double> b((size_t)mat.rows, 1.0), x((size_t)mat.rows, 0.0);
+    CGConfig cfg = {a.maxiter, a.tol, 1, a.timers ? 1 : 0};
+    bool first = true;
+    for (auto& m : a.modes) {
+        SpmvOperator* op = get_operator(m.c_str());
+        printf("\n=== CG with operator: %s (%s interface) ===\n", op->name, a.host ? "host" : "device");
+        if (!a.host && !op->run_device) {
+            fprintf(stderr, "[ERROR] Operator '%s' does not support device-native interface\n", op->name);
+            return EXIT_FAILURE;
+        }
+        if (op->init(&mat) != 0) { fprintf(stderr, "Failed to initialize operator '%s'\n", op->name); return EXIT_FAILURE; }
+        CGStats st;
+        CGConfig quiet = cfg;
+        quiet.verbose = 0;
+        printf("Warmup (3 runs)...\n");
+        for (int w = 0; w < 3; w++) {
+            std::fill(x.begin(), x.end(), 0.0);
+            int rc = a.host ? cg_solve(op, &mat, b.data(), x.data(), quiet, &st) : cg_solve_device(op, &mat, b.data(), x.data(), quiet, &st);
+            if (rc != 0) { fprintf(stderr, "CG solve failed\n"); return EXIT_FAILURE; }
+        }
+        std::fill(x.begin(), x.end(), 0.0);
+        printf("Running benchmark (%d runs)...\n", a.runs);
+        BenchmarkStats bs;
+        if (cg_benchmark_with_stats_device(op, &mat, b.data(), x.data(), cfg, a.runs, &bs, &st) != 0) {
+            fprintf(stderr, "CG benchmark failed for mode '%s'\n", op->name);
+            return EXIT_FAILURE;
+        }
+        printf("\n=== CG Results (%s) ===\n", op->name);
+        printf("Converged: %s in %d iterations, residual %.6e\n", st.converged ? "YES" : "NO", st.iterations, st.residual_norm);
+        printf("Time: median %.3f ms (mean %.3f, min %.3f, max %.3f, std %.3f; %d runs, %d outliers)\n", bs.median_ms,
+               bs.mean_ms, bs.min_ms, bs.max_ms, bs.std_dev_ms, bs.valid_runs, bs.outliers_removed);
+        printf("Sum(x):    %.16e\n", st.solution_sum);
+        printf("Norm2(x):  %.16e\n", st.solution_norm);
+        if (!a.json.empty()) {
+            std::string fn = a.json + "_" + m + ".json";
+            export_cg_json(fn.c_str(), m.c_str(), &mat, &bs, &st);
+        }
+        if (!a.csv.empty()) export_cg_csv(a.csv.c_str(), m.c_str(), &mat, &bs, &st, first);
+        first = false;
+        op->free();
+    }
+    free(mat.entries);
+    return EXIT_SUCCESS;
+}

@@ -275,7 +275,9 @@ extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long 
     long long p95_len = 1LL << p95_bin;
     if (p95_len > (long long)plan->max_row_len && plan->max_row_len > 0) p95_len = (long long)plan->max_row_len;
     int window = 3072;  // 48 KB of shared memory per CTA (values + gathered x) -> 4 CTAs / SM
-    long long rpb = window / (p95_len > 0 ? p95_len : 1);
+    long long typical = (long long)(2.0 * plan->mean_row_len + 0.999);
+    if (typical < p95_len) typical = p95_len;
+    long long rpb = window / (typical > 0 ? typical : 1);
     if (rpb > 512) rpb = 512;
     if (rpb < 8) rpb = 8;
     plan->rows_per_block = (int)rpb;

@@ -202,6 +202,7 @@ struct Workspace {
     int grid = 0, world = 0;
     const void* matrix_key = nullptr;  // entries pointer or operator pointer
     int matrix_nnz = 0;
+    bool synthetic = false;
     void release() {
         for (auto& w : ranks) { cudaSetDevice(w.dev); w.free_vectors(); }
         ranks.clear();
@@ -263,6 +264,7 @@ struct SolveOut {
     double phase_ms[T_N] = {0};
     int phase_cnt[T_N] = {0};
 };
+SolveOut g_last;  // per-phase event times of the most recent solve (enable_detailed_timers)
 
 // band descriptor of rank w with its halo wiring for this epoch
 void wire_band(const RankWs& w, b200_band* b, bool halos, uint32_t epoch) {
@@ -491,13 +493,19 @@ void partition(long long N, int P, int r, long long* nl, long long* off) {
 // (re)build the workspace for this matrix / world; returns 0 when ws is ready
 int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Engine* eng) {
     const long long N = mat->rows;
-    const void* key = fused_from_op ? (const void*)op : (mat->entries ? (const void*)mat->entries : (const void*)mat);
-    const bool same = ws.N == N && ws.grid == mat->grid_size && ws.world == g.world && ws.matrix_key == key &&
-                      ws.matrix_nnz == mat->nnz && !ws.ranks.empty() &&
-                      (!fused_from_op || ws.ranks[0].band.d_values == operator_band(op)->d_values);
+    // Workspace re-use between solves.  The vectors only depend on the shape; a band owned by the
+    // workspace is only trusted again when its content is fully determined by the shape (synthetic
+    // stencil) -- bands cut from caller-provided entries are rebuilt on every call, like the
+    // reference, which uploads its local CSR per solve (cg_solver_mgpu_partitioned.cu:303-343).
+    const void* key = (fused_from_op || !eng->fused) ? (const void*)op : (const void*)nullptr;
+    bool same = ws.N == N && ws.grid == mat->grid_size && ws.world == g.world && ws.matrix_key == key &&
+                ws.matrix_nnz == mat->nnz && !ws.ranks.empty();
+    if (same && fused_from_op) same = ws.ranks[0].band.d_values == operator_band(op)->d_values;
+    if (same && !fused_from_op && eng->fused) same = is_synthetic(mat) && ws.synthetic;
     if (!same) {
         ws.release();
         ws.N = N; ws.grid = mat->grid_size; ws.world = g.world; ws.matrix_key = key; ws.matrix_nnz = mat->nnz;
+        ws.synthetic = is_synthetic(mat);
         const int L = g.inited ? g.nlocal : 1;
         ws.ranks.resize(L);
         for (int l = 0; l < L; l++) {
@@ -588,6 +596,7 @@ int solve_single(SpmvOperator* op, MatrixData* mat, const double* b, double* x, 
     SolveOut o;
     int rc = eng.solve(b, x, cfg.max_iters, cfg.tolerance, cfg.verbose, cfg.enable_detailed_timers, tag, &o);
     if (rc) return rc;
+    g_last = o;
     fill_stats(o, stats);
     if (cfg.verbose >= 1) print_summary(tag, stats);
     return 0;
@@ -646,6 +655,7 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
     int rc = eng.solve(b, x, config.max_iters, config.tolerance, config.verbose, config.enable_detailed_timers,
                        "CG-MGPU", &o);
     if (rc) return rc;
+    g_last = o;
     memset(stats, 0, sizeof *stats);
     stats->iterations = o.iterations;
     stats->residual_norm = o.residual;
@@ -672,6 +682,17 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
         printf("[CG-MGPU] Total: %.3f ms\n", stats->time_total_ms);
     }
     return 0;
+}
+
+// Per-phase event times (ms) and launch counts of the most recent solve that ran with
+// enable_detailed_timers: [0] unused, [1] K1 SpMV+p.Ap, [2] reduce p.Ap, [3] K2 x/r update + r.r,
+// [4] reduce r.r, [5] K3 p update, [6] halo push, [7] residual init, [8] reduce r0.r0.
+extern "C" int b200_last_phase_times(double* ms9, int* count9) {
+    for (int t = 0; t < T_N; t++) {
+        if (ms9) ms9[t] = g_last.phase_ms[t];
+        if (count9) count9[t] = g_last.phase_cnt[t];
+    }
+    return T_N;
 }
 
 // Declared but never defined in the reference (cg_solver_mgpu.h:88-89, "full replication").

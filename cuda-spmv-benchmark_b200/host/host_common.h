@@ -81,4 +81,5 @@ void b200_mgpu_finalize(void);
 MatrixData b200_synthetic_stencil(int grid_size);
 int b200_set_tuning(int variant, int rows_per_item);
 void b200_get_tuning(int* variant, int* rows_per_item);
+int b200_last_phase_times(double* ms9, int* count9);
 }

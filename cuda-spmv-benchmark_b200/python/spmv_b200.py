@@ -112,7 +112,7 @@ C_SYMBOLS = [
     # extensions (host/host_common.h)
     "b200_operator_band", "b200_mgpu_init_single_process", "b200_mgpu_init_rank", "b200_mgpu_connect",
     "b200_mgpu_world", "b200_mgpu_rank", "b200_mgpu_finalize", "b200_synthetic_stencil", "b200_set_tuning",
-    "b200_get_tuning",
+    "b200_get_tuning", "b200_last_phase_times",
 ]
 # C++-linkage symbols of the reference API (Itanium mangling)
 CXX_SYMBOLS = {
@@ -205,6 +205,7 @@ def load():
     L.b200_synthetic_stencil.restype = MatrixData
     L.b200_synthetic_stencil.argtypes = [i32]
     L.b200_set_tuning.argtypes = [i32, i32]
+    L.b200_last_phase_times.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     # C++-linkage entry points
     L.build_csr_struct = getattr(L, CXX_SYMBOLS["build_csr_struct"])
     L.build_csr_struct.argtypes = [C.POINTER(MatrixData)]

@@ -1,0 +1,52 @@
+#!/bin/bash
+# Runs the REFERENCE's own CLI binaries (oracle/_ref/{generate_matrix,spmv_bench,cg_solver},
+# compiled from the reference sources by oracle/Makefile) on the GPU box and collects their
+# printed checksums / iteration counts into gpurun_out/ref_gpu.json -- the golden vectors that pin
+# the oracle's numeric functions (tests/test_oracle_golden.py).  Test infrastructure only.
+#   usage (on the GPU box, repo root):  bash oracle/run_ref_gpu.sh
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/ref_gpu
+mkdir -p "$OUT"
+python - <<'PY'
+import json, os, re, subprocess, sys, time
+sys.path.insert(0, "oracle")
+import orc
+out = "gpurun_out/ref_gpu"
+cases = []
+for n, center in ((81, -4.0), (64, 5.0), (512, 5.0), (1000, 5.0), (2000, 5.0)):
+    mtx = os.path.join(out, "s%d.mtx" % n)
+    if center == -4.0:
+        orc.write_mtx_stencil5(n, mtx, "-4.0", "-1.0")   # byte-identical to matrix/example81x81.mtx
+    else:
+        subprocess.run(["oracle/_ref/generate_matrix", str(n), mtx], check=True, stdout=subprocess.DEVNULL)
+    case = {"n": n, "center": center, "spmv": {}, "cg": {}}
+    r = subprocess.run(["oracle/_ref/spmv_bench", mtx, "--mode=stencil5-csr,cusparse-csr",
+                        "--json=%s/spmv_%d.json" % (out, n)], capture_output=True, text=True)
+    open(os.path.join(out, "spmv_%d.log" % n), "w").write(r.stdout + r.stderr)
+    for op in ("stencil5-csr", "cusparse-csr"):
+        p = "%s/spmv_%d_%s.json" % (out, n, op)
+        if os.path.exists(p):
+            j = json.load(open(p))
+            v = j["benchmark"]["validation"]
+            case["spmv"][op] = {"sum_y": v["sum_y"], "norm2_y": v["norm2_y"],
+                                "execution_time_ms": j["benchmark"]["performance"]["execution_time_ms"]}
+    for op in ("stencil5-csr", "cusparse-csr"):
+        r = subprocess.run(["oracle/_ref/cg_solver", mtx, "--mode=%s" % op, "--json=%s/cg_%d" % (out, n)],
+                           capture_output=True, text=True)
+        open(os.path.join(out, "cg_%d_%s.log" % (n, op)), "w").write(r.stdout + r.stderr)
+        p = "%s/cg_%d_%s.json" % (out, n, op)
+        if os.path.exists(p):
+            j = json.load(open(p))
+            case["cg"][op] = {"iterations": j["convergence"]["iterations"], "converged": j["convergence"]["converged"],
+                              "residual_norm": j["convergence"]["residual_norm"],
+                              "solution_sum": j["validation"]["solution_sum"],
+                              "solution_norm": j["validation"]["solution_norm"], "median_ms": j["timing"]["median_ms"]}
+    cases.append(case)
+    os.remove(mtx)
+gpu = subprocess.run(["nvidia-smi", "--query-gpu=name,driver_version", "--format=csv,noheader"],
+                     capture_output=True, text=True).stdout.strip()
+json.dump({"generator": "oracle/run_ref_gpu.sh: reference spmv_bench / cg_solver (oracle/_ref, -arch=sm_100) on " + gpu,
+           "cases": cases}, open("gpurun_out/ref_gpu.json", "w"), indent=1)
+print(json.dumps(cases)[:2000])
+PY

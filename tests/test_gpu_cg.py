@@ -1,0 +1,195 @@
+"""GPU parity: CG through the reference-facing entry points (cg_solve_device, cg_solve,
+cg_solve_mgpu_partitioned, the bench wrappers) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): same iteration count as the reference recurrence; final residual
+within 1e-10 relative of the oracle's; solution within 1e-10 relative L2 (the dot products are
+summed in a different -- fixed -- order than the reference's block tree, so the trajectories agree
+to rounding, not bit for bit); results reproducible bit for bit from run to run."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def solve_device(B, opname, hm, b, x0, tol=1e-6, max_iters=1000, timers=0, entry="cg_solve_device"):
+    L = B.load()
+    op = L.get_operator(opname)
+    assert op.contents.init(hm.ptr()) == 0
+    x = np.array(x0, dtype=np.float64, copy=True)
+    st = B.CGStats()
+    rc = getattr(L, entry)(op, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(max_iters, tol, 0, timers), C.byref(st))
+    assert rc == 0
+    return x, B.stats_dict(st), op
+
+
+def oracle_solve(orc, n, op, b, x0, center=5.0, tol=1e-6, max_iters=1000):
+    rp64, ci, va = orc.stencil5_csr_direct(n, center, -1.0)
+    return orc.cg_device(rp64.astype(np.int32), ci, va, n, op, b, x0, max_iters, tol)
+
+
+@pytest.mark.parametrize("n,iters", [(3, 3), (81, 18), (512, 17), (1000, None)])
+@pytest.mark.parametrize("opname", [b"stencil5-csr", b"cusparse-csr", b"ellpack", b"stencil5-ellpack"])
+def test_cg_solve_device_matches_oracle(B, orc, torch_cuda, n, iters, opname):
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    b, x0 = np.ones(N), np.zeros(N)
+    x, st, op = solve_device(B, opname, hm, b, x0)
+    xo, ro, _ = oracle_solve(orc, n, 1 if opname.startswith(b"stencil5") else 0, b, x0)
+    if iters is not None:
+        assert ro["iterations"] == iters
+    assert st["iterations"] == ro["iterations"] and st["converged"] == 1 == ro["converged"]
+    assert math.isclose(st["residual_norm"], ro["residual_norm"], rel_tol=1e-10)
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    assert math.isclose(st["solution_sum"], ro["solution_sum"], rel_tol=1e-12)
+    assert math.isclose(st["solution_norm"], ro["solution_norm"], rel_tol=1e-12)
+    assert math.isclose(st["solution_sum"], float(x.sum()), rel_tol=1e-12)
+    assert st["time_total_ms"] > 0
+    op.contents.free()
+
+
+def test_cg_from_mtx_file_bundled(B, orc, torch_cuda, tmp_path):
+    """config[0]: bundled 81x81 (centre -4) loaded from the .mtx, 40 iterations"""
+    p = str(tmp_path / "example81x81.mtx")
+    orc.write_mtx_stencil5(81, p, "-4.0", "-1.0")
+    hm = B.HostMatrix.from_mtx(p)
+    b, x0 = np.ones(6561), np.zeros(6561)
+    for opname in (b"stencil5-csr", b"cusparse-csr"):
+        x, st, op = solve_device(B, opname, hm, b, x0)
+        xo, ro, _ = oracle_solve(orc, 81, 1, b, x0, center=-4.0)
+        assert st["iterations"] == 40 == ro["iterations"] and st["converged"] == 1
+        assert math.isclose(st["residual_norm"], ro["residual_norm"], rel_tol=1e-10)
+        assert math.isclose(st["solution_sum"], -826.0838884, rel_tol=1e-9)
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+        op.contents.free()
+
+
+def test_cg_nonzero_guess_random_rhs_and_host_entry(B, orc, torch_cuda):
+    n = 200
+    N = n * n
+    rng = np.random.default_rng(42)
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    hm = B.HostMatrix.synthetic_stencil(n)
+    x, st, op = solve_device(B, b"stencil5-csr", hm, b, x0, tol=1e-9, entry="cg_solve")
+    xo, ro, _ = oracle_solve(orc, n, 1, b, x0, tol=1e-9)
+    assert st["iterations"] == ro["iterations"] and st["converged"] == 1
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    op.contents.free()
+
+
+def test_cg_max_iters_and_timers(B, orc, torch_cuda):
+    n = 300
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    b, x0 = np.ones(N), np.zeros(N)
+    x, st, op = solve_device(B, b"stencil5-csr", hm, b, x0, tol=1e-14, max_iters=5, timers=1)
+    xo, ro, hist = oracle_solve(orc, n, 1, b, x0, tol=1e-14, max_iters=5)
+    assert st["iterations"] == 5 == ro["iterations"] and st["converged"] == 0 == ro["converged"]
+    assert math.isclose(st["residual_norm"], ro["residual_norm"], rel_tol=1e-10)
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-12
+    assert st["time_spmv_ms"] > 0 and st["time_blas1_ms"] > 0 and st["time_reductions_ms"] > 0
+    assert st["time_spmv_ms"] + st["time_blas1_ms"] + st["time_reductions_ms"] <= st["time_total_ms"] * 1.05
+    op.contents.free()
+
+
+def test_cg_bitwise_reproducible(B, torch_cuda):
+    n = 700
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    b, x0 = np.ones(N), np.zeros(N)
+    x1, st1, op = solve_device(B, b"stencil5-csr", hm, b, x0)
+    x2, st2, op = solve_device(B, b"stencil5-csr", hm, b, x0)
+    assert np.array_equal(x1, x2) and st1["residual_norm"] == st2["residual_norm"]
+    assert st1["iterations"] == st2["iterations"]
+    op.contents.free()
+
+
+def test_cg_bench_wrapper(B, torch_cuda):
+    L = B.load()
+    n = 256
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    op = L.get_operator(b"stencil5-csr")
+    assert op.contents.init(hm.ptr()) == 0
+    b, x = np.ones(N), np.zeros(N)
+    bs, cs = B.BenchmarkStats(), B.CGStats()
+    rc = L.cg_benchmark_with_stats_device(op, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(), 5, C.byref(bs), C.byref(cs))
+    assert rc == 0 and 3 <= bs.valid_runs <= 5 and bs.min_ms <= bs.median_ms <= bs.max_ms
+    assert cs.converged == 1 and cs.iterations > 0
+    op.contents.free()
+
+
+@pytest.mark.parametrize("n,P", [(81, 2), (81, 4), (64, 8), (130, 3), (512, 4)])
+def test_cg_mgpu_partitioned_virtual_ranks(B, orc, torch_cuda, n, P):
+    """P row bands as P virtual ranks on one GPU: exercises partition, local CSR slices, peer halo
+    push, flag waits and the LL scalar exchange of the multi-GPU path without needing P GPUs."""
+    L = B.load()
+    N = n * n
+    devs = (C.c_int * P)(*([0] * P))
+    assert L.b200_mgpu_init_single_process(P, devs, n) == 0
+    try:
+        assert L.b200_mgpu_world() == P
+        hm = B.HostMatrix.synthetic_stencil(n)
+        b, x = np.ones(N), np.zeros(N)
+        st = B.CGStatsMultiGPU()
+        rc = L.cg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(timers=1), C.byref(st))
+        assert rc == 0
+        xo, ro, _ = oracle_solve(orc, n, 1, b, np.zeros(N))
+        rp64, ci, va = orc.stencil5_csr_direct(n)
+        xm, rm = orc.cg_mgpu(rp64.astype(np.int32), ci, va, n, P, b, np.zeros(N))
+        assert st.iterations == ro["iterations"] == rm["iterations"] and st.converged == 1
+        assert math.isclose(st.residual_norm, ro["residual_norm"], rel_tol=1e-10)
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+        assert math.isclose(st.solution_sum, float(x.sum()), rel_tol=1e-12)
+        assert st.time_total_ms > 0 and st.time_allgather_ms > 0
+        # a second solve re-uses the workspace and the epochs keep advancing
+        x2 = np.zeros(N)
+        st2 = B.CGStatsMultiGPU()
+        assert L.cg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x2.ctypes.data, B.cg_config(), C.byref(st2)) == 0
+        assert np.array_equal(x, x2) and st2.iterations == st.iterations
+    finally:
+        L.b200_mgpu_finalize()
+
+
+def test_cg_mgpu_from_mtx_entries(B, orc, torch_cuda, tmp_path):
+    """band slices cut from the host CSR (not generated): bundled matrix on 3 virtual ranks"""
+    L = B.load()
+    p = str(tmp_path / "example81x81.mtx")
+    orc.write_mtx_stencil5(81, p, "-4.0", "-1.0")
+    hm = B.HostMatrix.from_mtx(p)
+    devs = (C.c_int * 3)(0, 0, 0)
+    assert L.b200_mgpu_init_single_process(3, devs, 81) == 0
+    try:
+        b, x = np.ones(6561), np.zeros(6561)
+        st = B.CGStatsMultiGPU()
+        assert L.cg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(), C.byref(st)) == 0
+        assert st.iterations == 40 and st.converged == 1
+        assert math.isclose(st.solution_sum, -826.0838884, rel_tol=1e-9)
+    finally:
+        L.b200_mgpu_finalize()
+
+
+def test_halo_mgpu_operator(B, orc, torch_cuda):
+    """"stencil5-halo-mgpu" (declared-only in the reference): host vectors in/out over row bands"""
+    import os
+    L = B.load()
+    n = 96
+    N = n * n
+    os.environ["B200_GPUS"] = "3"
+    try:
+        hm = B.HostMatrix.synthetic_stencil(n)
+        op = L.get_operator(b"stencil5-halo-mgpu").contents
+        assert not op.run_device
+        assert op.init(hm.ptr()) == 0
+        rng = np.random.default_rng(9)
+        x = rng.standard_normal(N)
+        y = np.full(N, np.nan)
+        ms = C.c_double()
+        assert op.run_timed(x.ctypes.data, y.ctypes.data, C.byref(ms)) == 0
+        rp64, ci, va = orc.stencil5_csr_direct(n)
+        assert np.array_equal(y, orc.stencil5_spmv(rp64.astype(np.int32), ci, va, x, n))
+        op.free()
+    finally:
+        del os.environ["B200_GPUS"]
