@@ -43,9 +43,12 @@ def test_cg_solve_device_matches_oracle(B, orc, torch_cuda, n, iters, opname):
     assert st["iterations"] == ro["iterations"] and st["converged"] == 1 == ro["converged"]
     assert math.isclose(st["residual_norm"], ro["residual_norm"], rel_tol=1e-10)
     assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
-    assert math.isclose(st["solution_sum"], ro["solution_sum"], rel_tol=1e-12)
-    assert math.isclose(st["solution_norm"], ro["solution_norm"], rel_tol=1e-12)
+    # x agrees to 1e-10 relative, so its sum / norm agree to the same order; the device-side
+    # checksum itself must match a host sum of the returned x to rounding
+    assert math.isclose(st["solution_sum"], ro["solution_sum"], rel_tol=1e-9)
+    assert math.isclose(st["solution_norm"], ro["solution_norm"], rel_tol=1e-9)
     assert math.isclose(st["solution_sum"], float(x.sum()), rel_tol=1e-12)
+    assert math.isclose(st["solution_norm"], float(np.linalg.norm(x)), rel_tol=1e-12)
     assert st["time_total_ms"] > 0
     op.contents.free()
 

@@ -196,25 +196,40 @@ REF_GPU = os.path.join(GOLDEN, "ref_gpu.json")
 
 @pytest.mark.skipif(not os.path.exists(REF_GPU), reason="reference GPU outputs not captured yet")
 def test_oracle_matches_reference_gpu_outputs(orc, tmp_path):
-    """The reference's own CLIs (oracle/_ref/spmv_bench, cg_solver built from its sources) run on a
-    B200 by oracle/run_ref_gpu.sh: iteration counts must be equal, checksums agree to 1e-12 / 1e-9."""
+    """The reference's own CLIs (oracle/_ref/spmv_bench, cg_solver built from its sources) were run on
+    a B200 by oracle/run_ref_gpu.sh.  Their printed checksums / iteration counts / residuals pin the
+    oracle's arithmetic: BIT-EXACT for the stencil5-csr operator, 1e-9 for cusparse-csr (library order).
+
+    Quirk reproduced here: the reference cg_solver CLI does not reset x between its warm-up solves and
+    the benchmarked solve (src/main/cg_solver.cu:155-173: cg_benchmark_with_stats_device backs up the
+    warm-up SOLUTION as its initial guess), so the numbers it prints belong to a warm restart:
+    CG(x0 = CG(x0 = 0))."""
     ref = json.load(open(REF_GPU))
+    assert len(ref["cases"]) >= 4
     for case in ref["cases"]:
         n, center = case["n"], case["center"]
         rp64, ci, va = orc.stencil5_csr_direct(n, center, -1.0)
         rp = rp64.astype(np.int32)
         N = n * n
-        if "spmv" in case:
-            y = orc.stencil5_spmv(rp, ci, va, np.ones(N), n)
-            for opname, s in case["spmv"].items():
-                assert math.isclose(float(y.sum()), s["sum_y"], rel_tol=1e-13, abs_tol=1e-9), (n, opname)
-                assert math.isclose(math.sqrt(float((y * y).sum())), s["norm2_y"], rel_tol=1e-12), (n, opname)
-        if "cg" in case:
-            for opname, c in case["cg"].items():
-                op = 1 if opname.startswith("stencil5") else 0
-                x, res, _ = orc.cg_device(rp, ci, va, n, op, np.ones(N), np.zeros(N))
-                assert res["iterations"] == c["iterations"], (n, opname)
-                assert res["converged"] == int(c["converged"])
-                assert math.isclose(res["residual_norm"], c["residual_norm"], rel_tol=1e-6), (n, opname)
-                assert math.isclose(res["solution_sum"], c["solution_sum"], rel_tol=1e-10), (n, opname)
-                assert math.isclose(res["solution_norm"], c["solution_norm"], rel_tol=1e-10), (n, opname)
+        y = orc.stencil5_spmv(rp, ci, va, np.ones(N), n)
+        for opname, s in case["spmv"].items():
+            assert float(y.sum()) == s["sum_y"], (n, opname)
+            ssq = 0.0
+            for v in y:  # host loop of src/main/main.cu:177-183 (index order, mul then add)
+                ssq += v * v
+            assert math.sqrt(ssq) == s["norm2_y"], (n, opname)
+        for opname, c in case["cg"].items():
+            op = 1 if opname.startswith("stencil5") else 0
+            x1, res1, _ = orc.cg_device(rp, ci, va, n, op, np.ones(N), np.zeros(N))
+            x2, res, _ = orc.cg_device(rp, ci, va, n, op, np.ones(N), x1)
+            assert res["iterations"] == c["iterations"], (n, opname)
+            assert res["converged"] == int(c["converged"])
+            if op == 1:
+                # printed with %.15e (16 significant digits): equal to the printed precision
+                assert float("%.15e" % res["residual_norm"]) == c["residual_norm"], (n, opname)
+                assert res["solution_sum"] == c["solution_sum"], (n, opname)
+                assert res["solution_norm"] == c["solution_norm"], (n, opname)
+            else:
+                assert math.isclose(res["residual_norm"], c["residual_norm"], rel_tol=1e-9), (n, opname)
+                assert math.isclose(res["solution_sum"], c["solution_sum"], rel_tol=1e-12), (n, opname)
+                assert math.isclose(res["solution_norm"], c["solution_norm"], rel_tol=1e-12), (n, opname)
