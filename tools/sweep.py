@@ -24,7 +24,9 @@ def dptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def timeit(fn, reps=10, warm=3):
+def timeit(fn, reps=7, warm=3, batch=4):
+    """median / best time of one launch; `batch` back-to-back launches per event pair so that the
+    launch latency of an idle GPU is not charged to the kernel"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -32,10 +34,11 @@ def timeit(fn, reps=10, warm=3):
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(batch):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / batch)
     ts.sort()
     return ts[len(ts) // 2], ts[0]
 
@@ -44,7 +47,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=10000)
     ap.add_argument("--what", default="stencil,cg,csr,ell")
-    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7")
+    ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10,11")
     ap.add_argument("--rows", default="8,16,32,64,128")
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     a = ap.parse_args()
