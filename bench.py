@@ -170,18 +170,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        handle = (C.c_ubyte * 64)()
-        rc = L.b200_mgpu_init_rank(rank, world, local_rank, n, handle)
-        if rc:
-            raise SystemExit("b200_mgpu_init_rank rc=%d" % rc)
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
-        allh = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        raw = torch.cat(allh).cpu().numpy().tobytes()
-        blob = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
-        rc = L.b200_mgpu_connect(blob)
-        if rc:
-            raise SystemExit("b200_mgpu_connect rc=%d" % rc)
+        import mgpu_bootstrap
+        mgpu_bootstrap.connect(L, dist, rank, world, local_rank, n)
         dist.barrier()
 
     def barrier():
@@ -191,9 +181,8 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     mat = B.HostMatrix.synthetic_stencil(n)
-    nl, off = (N // world, rank * (N // world))
-    if rank == world - 1:
-        nl = N - off
+    import mgpu_bootstrap
+    nl, off = mgpu_bootstrap.partition(N, world, rank)
     # pinned host buffers of the local slice; the solver only touches [off, off+nl) of b and x
     b_host = torch.ones(nl, dtype=torch.float64).pin_memory()
     x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()

@@ -52,21 +52,21 @@ struct Variant {
 };
 // keep in sync with the dispatch switch below
 const Variant kVariants[] = {
-    {2, 4, 4, "v0: 64-col strips (2 cols/lane), 4 warps/CTA, 4-stage ring"},
+    {2, 2, 3, "v0 (default): 64-col strips (2 cols/lane), 2 warps/CTA, 3-stage ring"},
     {1, 4, 4, "v1: 32-col strips (1 col/lane), 4 warps/CTA, 4-stage ring"},
     {2, 8, 4, "v2: 64-col strips, 8 warps/CTA, 4-stage ring"},
     {4, 4, 3, "v3: 128-col strips (4 cols/lane), 4 warps/CTA, 3-stage ring"},
     {2, 4, 3, "v4: 64-col strips, 4 warps/CTA, 3-stage ring"},
     {2, 2, 4, "v5: 64-col strips, 2 warps/CTA, 4-stage ring"},
     {4, 2, 3, "v6: 128-col strips, 2 warps/CTA, 3-stage ring"},
-    {2, 2, 3, "v7: 64-col strips, 2 warps/CTA, 3-stage ring"},
+    {2, 4, 4, "v7: 64-col strips, 4 warps/CTA, 4-stage ring"},
     {2, 1, 4, "v8: 64-col strips, 1 warp/CTA, 4-stage ring"},
     {4, 4, 2, "v9: 128-col strips, 4 warps/CTA, 2-stage ring"},
     {4, 1, 3, "v10: 128-col strips, 1 warp/CTA, 3-stage ring"},
     {2, 4, 2, "v11: 64-col strips, 4 warps/CTA, 2-stage ring"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-const int kDefaultRowsPerItem = 32;
+const int kDefaultRowsPerItem = 16;
 
 struct Geometry {
     Stencil5Args a;
@@ -161,12 +161,12 @@ int launch_variant(int v, const Geometry& g, cudaStream_t s) {
         case 4: return launch_one<MODE, 2, 4, 3, CG>(g, s);
         case 5: return launch_one<MODE, 2, 2, 4, CG>(g, s);
         case 6: return launch_one<MODE, 4, 2, 3, CG>(g, s);
-        case 7: return launch_one<MODE, 2, 2, 3, CG>(g, s);
+        case 7: return launch_one<MODE, 2, 4, 4, CG>(g, s);
         case 8: return launch_one<MODE, 2, 1, 4, CG>(g, s);
         case 9: return launch_one<MODE, 4, 4, 2, CG>(g, s);
         case 10: return launch_one<MODE, 4, 1, 3, CG>(g, s);
         case 11: return launch_one<MODE, 2, 4, 2, CG>(g, s);
-        default: return launch_one<MODE, 2, 4, 4, CG>(g, s);
+        default: return launch_one<MODE, 2, 2, 3, CG>(g, s);
     }
 }
 

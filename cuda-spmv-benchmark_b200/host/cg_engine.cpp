@@ -372,6 +372,8 @@ struct Engine {
 
         // ---- iterations (cg_solver.cu:538-638)
         const int lag = verbose >= 2 ? 0 : kLag;
+        const size_t loop_mark0 = pt.used;            // first phase mark of the iteration loop
+        const size_t marks_per_iter = multi ? 6 : 5;  // K1, R, K2, R, K3 (+ halo push)
         int launched = 0;
         bool done = false;
         for (int it = 0; it < max_iters && !done; it++) {
@@ -450,6 +452,9 @@ struct Engine {
         if (pt.on) {
             B200_CUDA(cudaSetDevice(w0.dev));
             for (size_t k = 1; k < pt.used; k++) {
+                // launches enqueued after convergence (the host polls kLag iterations behind) are
+                // no-ops on the device: keep them out of the per-phase times and launch counts
+                if (k >= loop_mark0 && (k - loop_mark0) / marks_per_iter >= (size_t)out->iterations) break;
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, w0.phase_ev[k - 1], w0.phase_ev[k]);
                 out->phase_ms[pt.tags[k]] += ms;

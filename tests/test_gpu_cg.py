@@ -41,7 +41,9 @@ def test_cg_solve_device_matches_oracle(B, orc, torch_cuda, n, iters, opname):
     if iters is not None:
         assert ro["iterations"] == iters
     assert st["iterations"] == ro["iterations"] and st["converged"] == 1 == ro["converged"]
-    assert math.isclose(st["residual_norm"], ro["residual_norm"], rel_tol=1e-10)
+    # "final residual within 1e-10 relative": relative to the initial residual (a residual that has
+    # dropped to rounding level, as on the 3x3 grid, has no meaningful digits of its own)
+    assert abs(st["residual_norm"] - ro["residual_norm"]) <= 1e-10 * max(ro["residual_norm"], ro["b_norm"] * 1e-6)
     assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
     # x agrees to 1e-10 relative, so its sum / norm agree to the same order; the device-side
     # checksum itself must match a host sum of the returned x to rounding
