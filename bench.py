@@ -261,6 +261,8 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("stencil5_dot_dram_bytes_per_launch_%d" % n)
+            if traffic is not None:  # captured on the full matrix: scale to this rank's band
+                traffic = traffic * nnz_local / float(5 * N - 4 * n)
         except Exception:
             traffic = None
     line = {

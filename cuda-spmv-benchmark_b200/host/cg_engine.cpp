@@ -325,6 +325,15 @@ struct Engine {
             B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
         }
         for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
+        if (multi) {
+            // Align the ranks before the clock starts (the reference does MPI_Barrier right before its
+            // start event, cg_solver_mgpu_partitioned.cu:405-413): an empty rank-exchange reduction is
+            // a device-side barrier over peer memory.  Without it a rank whose upload finished early
+            // would count its neighbours' PCIe time as solver time.
+            int zero[kMaxRanks] = {0};
+            if (for_ranks_reduce(3, tol, zero, false, ++g.red_epoch)) return 1;
+            for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
+        }
 
         PhaseTimer pt;
         pt.w = &ws.ranks[0];
