@@ -230,25 +230,15 @@ extern "C" int b200_spmv_stencil5_halo(const int* d_row_ptr, const int* d_col_id
 // generic CSR / ELLPACK
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kCsrThreads = 256;
+constexpr int kCsrWarps = 8;
 
 int launch_csr(const CsrArgs& a, cudaStream_t s) {
     if (a.n_rows == 0) return B200_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(csr_adaptive_kernel<kCsrThreads>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            snprintf(g_err, sizeof g_err, "csr: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return B200_ENODEV;
-        }
-        attr_set = true;
-    }
-    const long long blocks = (a.n_rows + a.rows_per_block - 1) / a.rows_per_block;
+    const long long rows_per_cta = 32LL * kCsrWarps;
+    const long long blocks = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
     if (blocks > 2147483647LL) return fail(B200_EINVAL, "csr: too many row blocks");
-    csr_adaptive_kernel<kCsrThreads><<<(unsigned)blocks, kCsrThreads, (size_t)a.window * 16, s>>>(a);
-    return check_launch("csr_adaptive_kernel");
+    csr_warp_stream_kernel<kCsrWarps><<<(unsigned)blocks, kCsrWarps * 32, 0, s>>>(a);
+    return check_launch("csr_warp_stream_kernel");
 }
 }  // namespace
 
@@ -275,21 +265,15 @@ extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long 
     memcpy(plan->hist, h, 33 * sizeof(unsigned long long));
     plan->max_row_len = h[33];
     plan->mean_row_len = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
-    // Block shape from the histogram: the window holds rows_per_block rows of the 95th-percentile
-    // length; blocks whose rows are longer than the window fall back to warp-per-row at run time.
-    unsigned long long acc = 0, target = (unsigned long long)(0.95 * (double)n_rows);
-    int p95_bin = 0;
-    for (int b = 0; b < 33; b++) { acc += h[b]; if (acc >= target) { p95_bin = b; break; } }
-    long long p95_len = 1LL << p95_bin;
-    if (p95_len > (long long)plan->max_row_len && plan->max_row_len > 0) p95_len = (long long)plan->max_row_len;
-    int window = 3072;  // 48 KB of shared memory per CTA (values + gathered x) -> 4 CTAs / SM
-    long long typical = (long long)(2.0 * plan->mean_row_len + 0.999);
-    if (typical < p95_len) typical = p95_len;
-    long long rpb = window / (typical > 0 ? typical : 1);
-    if (rpb > 512) rpb = 512;
-    if (rpb < 8) rpb = 8;
-    plan->rows_per_block = (int)rpb;
-    plan->window = window;
+    // Long-row threshold from the histogram: 32-row groups whose mean row length exceeds it are
+    // processed warp-per-row, everything else by the bit-exact stream path.  A matrix dominated by
+    // long rows (median bin above 64 entries) gets a lower threshold so that its groups vectorise.
+    unsigned long long acc = 0, half = (unsigned long long)(0.5 * (double)n_rows);
+    int median_bin = 0;
+    for (int b = 0; b < 33; b++) { acc += h[b]; if (acc >= half) { median_bin = b; break; } }
+    plan->rows_per_block = 32 * kCsrWarps;
+    plan->window = 256;
+    plan->vector_threshold = (median_bin > 6) ? 48 : 96;
     return B200_OK;
 }
 
@@ -299,7 +283,7 @@ extern "C" int b200_spmv_csr(const b200_csr_plan* plan, const int* d_row_ptr, co
     if (!plan || !d_row_ptr || !d_x || !d_y) return fail(B200_EINVAL, "csr: NULL argument");
     CsrArgs a;
     a.row_ptr = d_row_ptr; a.col_idx = d_col_idx; a.values = d_values; a.x = d_x; a.y = d_y;
-    a.n_rows = n_rows; a.ell_width = 0; a.rows_per_block = plan->rows_per_block; a.window = plan->window;
+    a.n_rows = n_rows; a.ell_width = 0; a.vector_threshold = plan->vector_threshold > 0 ? plan->vector_threshold : 96;
     a.alpha = alpha; a.beta = beta;
     return launch_csr(a, (cudaStream_t)stream);
 }
@@ -310,11 +294,7 @@ extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, c
     if (width < 1 || width > 1000) return fail(B200_EINVAL, "ellpack: width outside [1, MAX_WIDTH]");
     CsrArgs a;
     a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
-    a.n_rows = n_rows; a.ell_width = width; a.window = 3072;
-    int rpb = a.window / width;
-    if (rpb > 512) rpb = 512;
-    if (rpb < 1) rpb = 1;
-    a.rows_per_block = rpb;
+    a.n_rows = n_rows; a.ell_width = width; a.vector_threshold = 1 << 20;  // ELLPACK rows are uniform: always stream
     a.alpha = alpha; a.beta = beta;
     return launch_csr(a, (cudaStream_t)stream);
 }

@@ -5,17 +5,20 @@
 // (include/spmv_ellpack.h:28-51).  Semantics = the reference's scalar CSR kernel
 // (src/solvers/cg_solver_mgpu_partitioned.cu:40-56): sum_k fma(v[k], x[col[k]], sum), k ascending.
 //
-// Scheme (picked per matrix from a row-length histogram taken on the device at plan time):
-//   * STREAM blocks: a CTA owns ROWS consecutive rows whose non-zeros fit its shared-memory
-//     window.  Phase 1 streams col_idx / values of the whole block with fully coalesced loads
-//     (independent of row boundaries) and gathers x[col]; phase 2 is one thread per row adding
-//     its products from shared memory in k order -- bit-identical to the scalar reference order,
-//     while HBM only ever sees contiguous 128-byte bursts (the scalar kernel issues 12-byte
-//     strided requests per lane).
-//   * VECTOR rows: if a block does not fit (long rows), its rows are processed warp-per-row with
-//     lanes striding over the row and a fixed-order butterfly sum (order differs from the scalar
-//     reference => equal only to rounding, documented tolerance 1e-12 relative).
-// ELLPACK (row-major, padding index -1) reuses the stream path with row_ptr[r] = r * width.
+// Scheme ("warp-stream", chosen per 32-row group from the row lengths; the per-matrix row-length
+// histogram taken at plan time sets the long-row threshold):
+//   * A WARP owns 32 consecutive rows.  Their non-zeros are one contiguous range of col_idx /
+//     values, which the warp sweeps in windows of 256 entries with perfectly coalesced loads
+//     (lane k, k+32, ... -- independent of where rows begin), gathers x[col] for all of them at
+//     once (8 independent loads per lane in flight) and parks value and x side by side in its
+//     private shared-memory slice.  Then each lane adds the products of ITS row that fall into the
+//     window, in k order, carrying the running sum across windows.  The result is bit-identical to
+//     the scalar reference order, there is no block-wide barrier (only __syncwarp), and HBM only
+//     sees full-line bursts -- the scalar kernel issues strided 12-byte requests per lane.
+//   * Groups whose rows are long (more than `vector_threshold` entries per row on average) are
+//     processed warp-per-row instead: lanes stride over the row, fixed-order butterfly sum (order
+//     differs from the scalar reference => equal to rounding only, documented tolerance 1e-12).
+// ELLPACK (row-major, padding index -1) is the same kernel with row_ptr[r] = r * width.
 #pragma once
 #include "common.cuh"
 
@@ -29,8 +32,7 @@ struct CsrArgs {
     double* y;
     long long n_rows;
     int ell_width;
-    int rows_per_block;
-    int window;  // shared-memory capacity in non-zeros
+    int vector_threshold;  // mean entries per row of a 32-row group above which it goes warp-per-row
     double alpha, beta;
 };
 
@@ -55,52 +57,81 @@ __global__ void row_length_histogram_kernel(const int* __restrict__ row_ptr, lon
     if (threadIdx.x == 0) atomicMax(max_len, (unsigned long long)smax);
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) csr_adaptive_kernel(const CsrArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sv = reinterpret_cast<double*>(smem_raw);  // values
-    double* sx = sv + a.window;                         // gathered x (NaN-safe skip flag via col<0)
-    const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrArgs a) {
+    constexpr int WIN = 256;  // entries per window = 8 per lane
+    __shared__ double sv[WARPS][WIN];
+    __shared__ double sx[WARPS][WIN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = ((long long)blockIdx.x * WARPS + warp) * 32;
     if (r0 >= a.n_rows) return;
-    const long long r1 = min(r0 + (long long)a.rows_per_block, a.n_rows);
+    const long long r = r0 + lane;
+    const bool live = r < a.n_rows;
     const bool ell = (a.row_ptr == nullptr);
-    const long long k0 = ell ? r0 * a.ell_width : (long long)a.row_ptr[r0];
-    const long long k1 = ell ? r1 * a.ell_width : (long long)a.row_ptr[r1];
-    const long long cnt = k1 - k0;
+    long long s = 0, e = 0;
+    if (live) {
+        s = ell ? r * a.ell_width : (long long)__ldg(a.row_ptr + r);
+        e = ell ? (r + 1) * a.ell_width : (long long)__ldg(a.row_ptr + r + 1);
+    }
+    const long long k_begin = __shfl_sync(B200_FULL, s, 0);
+    long long k_end = live ? e : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(B200_FULL, k_end, o);
+        k_end = t > k_end ? t : k_end;
+    }
+    const long long rows_here = min(32LL, a.n_rows - r0);
+    double sum = 0.0;
 
-    if (cnt <= a.window) {
-        // ---- STREAM: coalesced sweep over the block's non-zeros
-        for (long long k = threadIdx.x; k < cnt; k += THREADS) {
-            const int c = __ldcs(a.col_idx + k0 + k);
-            const double v = __ldcs(a.values + k0 + k);
-            sv[k] = (c >= 0) ? v : 0.0;
-            sx[k] = (c >= 0) ? __ldg(a.x + c) : 0.0;  // padding: 0*0, exact no-op under fma
+    if (k_end - k_begin <= (long long)a.vector_threshold * rows_here) {
+        // ---- stream: windows of 256 entries, lane-per-row accumulation in k order
+        double* mv = sv[warp];
+        double* mx = sx[warp];
+        for (long long w = k_begin; w < k_end; w += WIN) {
+            int c[8];
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const long long k = w + u * 32 + lane;
+                c[u] = -1;
+                v[u] = 0.0;
+                if (k < k_end) {
+                    c[u] = __ldcs(a.col_idx + k);
+                    v[u] = __ldcs(a.values + k);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                // padding / out-of-window: 0 * 0, an exact no-op under fma
+                const double xv = (c[u] >= 0) ? __ldg(a.x + c[u]) : 0.0;
+                mv[u * 32 + lane] = (c[u] >= 0) ? v[u] : 0.0;
+                mx[u * 32 + lane] = xv;
+            }
+            __syncwarp();
+            const long long lo = s > w ? s : w;
+            const long long hi = e < w + WIN ? e : w + WIN;
+            for (long long k = lo; k < hi; k++) sum = fma(mv[k - w], mx[k - w], sum);
+            __syncwarp();
         }
-        __syncthreads();
-        for (long long r = r0 + threadIdx.x; r < r1; r += THREADS) {
-            const long long s = (ell ? r * a.ell_width : (long long)a.row_ptr[r]) - k0;
-            const long long e = (ell ? (r + 1) * a.ell_width : (long long)a.row_ptr[r + 1]) - k0;
-            double sum = 0.0;
-            for (long long k = s; k < e; k++) sum = fma(sv[k], sx[k], sum);
+        if (live) {
             if (a.beta == 0.0) a.y[r] = a.alpha * sum;
             else a.y[r] = fma(a.alpha, sum, a.beta * a.y[r]);
         }
     } else {
-        // ---- VECTOR: warp per row
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (long long r = r0 + warp; r < r1; r += THREADS / 32) {
-            const long long s = ell ? r * a.ell_width : (long long)a.row_ptr[r];
-            const long long e = ell ? (r + 1) * a.ell_width : (long long)a.row_ptr[r + 1];
-            double sum = 0.0;
-            for (long long k = s + lane; k < e; k += 32) {
-                const int c = a.col_idx[k];
-                if (c >= 0) sum = fma(a.values[k], __ldg(a.x + c), sum);
+        // ---- vector: the warp walks its rows one by one
+        for (int q = 0; q < rows_here; q++) {
+            const long long qs = __shfl_sync(B200_FULL, s, q), qe = __shfl_sync(B200_FULL, e, q);
+            double part = 0.0;
+            for (long long k = qs + lane; k < qe; k += 32) {
+                const int cc = a.col_idx[k];
+                if (cc >= 0) part = fma(a.values[k], __ldg(a.x + cc), part);
             }
-            sum = warp_sum(sum);
-            if (lane == 0) {
-                if (a.beta == 0.0) a.y[r] = a.alpha * sum;
-                else a.y[r] = fma(a.alpha, sum, a.beta * a.y[r]);
-            }
+            part = warp_sum(part);
+            if (lane == q) sum = part;
+        }
+        if (live) {
+            if (a.beta == 0.0) a.y[r] = a.alpha * sum;
+            else a.y[r] = fma(a.alpha, sum, a.beta * a.y[r]);
         }
     }
 }

@@ -87,7 +87,8 @@ class Band(C.Structure):  # b200_band, include/b200_kernels.h
 
 
 class CsrPlan(C.Structure):
-    _fields_ = [("rows_per_block", C.c_int), ("window", C.c_int), ("hist", C.c_ulonglong * 33),
+    _fields_ = [("rows_per_block", C.c_int), ("window", C.c_int), ("vector_threshold", C.c_int),
+                ("reserved", C.c_int), ("hist", C.c_ulonglong * 33),
                 ("max_row_len", C.c_ulonglong), ("mean_row_len", C.c_double)]
 
 
