@@ -388,6 +388,21 @@ extern "C" int b200_cg_update_p(long long n, const void* d_scalars, const double
     return check_launch("cg_update_p_kernel");
 }
 
+extern "C" int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p, int halo,
+                                     double* d_dst_prev, double* d_dst_next, uint32_t* d_flag_prev,
+                                     uint32_t* d_flag_next, uint32_t epoch, void* d_my_xchg, b200_stream stream) {
+    if (!d_scalars || !d_r || !d_p || !d_my_xchg || halo < 1 || n < halo) return fail(B200_EINVAL, "cg_update_p_push: bad argument");
+    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "cg_update_p_push: NULL flag");
+    HaloPushArgs a;
+    a.v_local = d_p; a.n_local = n; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
+    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
+    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
+    a.sc = static_cast<const CGScalars*>(d_scalars);
+    const int grid = blas1_grid(n, 1);
+    cg_update_p_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, a.sc, d_r, d_p, a);
+    return check_launch("cg_update_p_push_kernel");
+}
+
 extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
                               void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
                               uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream) {

@@ -369,4 +369,46 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
     }
 }
 
+// K3 with the halo push fused in (multi-GPU): p = r + beta p, and the CTAs that produce the first /
+// last `halo` elements store them straight into the neighbours' landing buffers over NVLink.  The
+// last CTA to finish (device-scope counter after a system fence) release-stores the arrival epoch
+// into both neighbours' flags.  One launch less on the critical path than K3 + halo_push_kernel.
+__global__ void __launch_bounds__(256) cg_update_p_push_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                               const double* __restrict__ r, double* __restrict__ p,
+                                                               const HaloPushArgs h) {
+    if (sc->converged) return;
+    const double beta = sc->beta;
+    const long long tile = 1024;
+    const long long next_lo = n - h.halo;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        double pv[4], rv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) { pv[u] = __ldcs(p + i); rv[u] = __ldcs(r + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) {
+                const double v = fma(beta, pv[u], rv[u]);
+                p[i] = v;
+                if (h.dst_prev != nullptr && i < h.halo) h.dst_prev[i] = v;
+                if (h.dst_next != nullptr && i >= next_lo) h.dst_next[i - next_lo] = v;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(&h.push_count[0], 1u) + 1u;
+        if (done == gridDim.x) {
+            h.push_count[0] = 0;
+            __threadfence_system();
+            if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, h.epoch);
+            if (h.dst_next != nullptr) st_release_sys(h.flag_next, h.epoch);
+        }
+    }
+}
+
 }  // namespace b200

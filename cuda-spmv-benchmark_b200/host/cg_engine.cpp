@@ -382,7 +382,7 @@ struct Engine {
         // ---- iterations (cg_solver.cu:538-638)
         const int lag = verbose >= 2 ? 0 : kLag;
         const size_t loop_mark0 = pt.used;            // first phase mark of the iteration loop
-        const size_t marks_per_iter = multi ? 6 : 5;  // K1, R, K2, R, K3 (+ halo push)
+        const size_t marks_per_iter = 5;              // K1, R, K2, R, K3 (halo push fused into K3)
         int launched = 0;
         bool done = false;
         for (int it = 0; it < max_iters && !done; it++) {
@@ -414,18 +414,27 @@ struct Engine {
             if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch)) return 1;  // convergence, beta
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_RED_RR);
-            for (auto& w : ws.ranks) {  // K3: p = r + beta p
-                B200_CUDA(cudaSetDevice(w.dev));
-                B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
+            if (!multi) {
+                for (auto& w : ws.ranks) {  // K3: p = r + beta p
+                    B200_CUDA(cudaSetDevice(w.dev));
+                    B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
+                }
+            } else {
+                // K3 + halo push in one launch: the edge elements of the new p go straight into the
+                // neighbours' landing buffers, the last CTA publishes the arrival epoch
+                const uint32_t e = ++g.halo_epoch;
+                for (auto& w : ws.ranks) {
+                    B200_CUDA(cudaSetDevice(w.dev));
+                    double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
+                    double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
+                    uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
+                    uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
+                    B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, ws.grid, dprev, dnext, fprev, fnext, e,
+                                                 g.xchg[w.rank], w.st));
+                }
             }
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_P);
-            if (multi) {
-                const uint32_t e = ++g.halo_epoch;
-                for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_K(push_halo(w, w.p, e, w.scalars)); }
-                B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-                pt.mark(T_HALO);
-            }
             RankWs& w0 = ws.ranks[0];
             B200_CUDA(cudaSetDevice(w0.dev));
             B200_CUDA(cudaEventRecord(iter_event(w0, it), w0.st));

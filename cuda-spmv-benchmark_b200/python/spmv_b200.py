@@ -100,6 +100,7 @@ C_SYMBOLS = [
     "b200_stencil5_variant_info", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
+    "b200_cg_update_p_push",
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
@@ -168,6 +169,7 @@ def load():
     L.b200_cg_update_xr.argtypes = [ll, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.b200_cg_update_p.argtypes = [ll, vp, vp, vp, vp]
     L.b200_cg_reduce.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp]
+    L.b200_cg_update_p_push.argtypes = [ll, vp, vp, vp, i32, vp, vp, vp, vp, C.c_uint32, vp, vp]
     L.b200_dot_partials.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.b200_residual_init_generic.argtypes = [ll, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.b200_checksum_partials.argtypes = [ll, vp, vp, vp, C.POINTER(i32), vp]

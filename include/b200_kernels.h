@@ -162,6 +162,11 @@ int b200_checksum_partials(long long n, const double* d_x, double* d_psum, doubl
 int b200_halo_push(const double* d_v_local, long long n_local, int halo, double* d_dst_prev,
                    double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next, uint32_t epoch,
                    void* d_my_xchg, const void* d_scalars, b200_stream stream);
+/* K3 with the halo push fused in: p = r + beta p, the first / last `halo` elements are also stored
+ * into the neighbours' landing buffers and the arrival epoch is published by the last CTA. */
+int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p, int halo,
+                          double* d_dst_prev, double* d_dst_next, uint32_t* d_flag_prev,
+                          uint32_t* d_flag_next, uint32_t epoch, void* d_my_xchg, b200_stream stream);
 /* offsets of the halo flags inside an exchange area */
 size_t b200_xchg_flag_prev_offset(void);
 size_t b200_xchg_flag_next_offset(void);
