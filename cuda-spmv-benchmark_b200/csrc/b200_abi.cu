@@ -10,6 +10,7 @@
 #include "cg_kernels.cuh"
 #include "csr_ell.cuh"
 #include "generate.cuh"
+#include "ingest.cuh"
 #include "stencil5.cuh"
 #include "stencil_layout.h"
 
@@ -514,4 +515,130 @@ extern "C" int b200_fill(double* d_p, long long n, double value, b200_stream str
     if (n <= 0) return B200_OK;
     fill_kernel<<<gen_grid(n), 256, 0, (cudaStream_t)stream>>>(d_p, n, value);
     return check_launch("fill_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side ingest: Matrix Market entry text -> COO, COO -> CSR  
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+// exclusive scan of n ints/long longs into d_out (long long); *d_total (device) receives the sum
+template <typename T>
+int exclusive_scan(const T* d_in, long long* d_out, long long n, long long* d_total, cudaStream_t s) {
+    const long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    DevBuf sums;
+    if (sums.alloc((size_t)(tiles > 0 ? tiles : 1) * sizeof(long long)) != cudaSuccess) return fail(B200_ENOMEM, "scan: cudaMalloc");
+    if (tiles > 0) {
+        scan_tiles_kernel<T><<<(unsigned)tiles, 256, 0, s>>>(d_in, d_out, n, sums.as<long long>());
+        int rc = check_launch("scan_tiles_kernel");
+        if (rc) return rc;
+    }
+    scan_tile_sums_kernel<<<1, 1024, 0, s>>>(sums.as<long long>(), tiles, d_total);
+    int rc = check_launch("scan_tile_sums_kernel");
+    if (rc) return rc;
+    if (tiles > 0) {
+        scan_add_offsets_kernel<<<(unsigned)tiles, 256, 0, s>>>(d_out, n, sums.as<long long>());
+        rc = check_launch("scan_add_offsets_kernel");
+        if (rc) return rc;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);  // sums is freed on return
+    if (e != cudaSuccess) return fail(B200_ECUDA, "scan: %s", cudaGetErrorString(e));
+    return B200_OK;
+}
+}  // namespace
+
+extern "C" int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int* d_row_ptr, int* d_col_idx,
+                               double* d_values, b200_stream stream) {
+    if ((!d_entries && nnz > 0) || !d_row_ptr || rows < 0 || nnz < 0 || nnz > 2147483647LL)
+        return fail(B200_EINVAL, "coo_to_csr: bad argument");
+    if (nnz > 0 && (!d_col_idx || !d_values)) return fail(B200_EINVAL, "coo_to_csr: NULL output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const EntryPOD* e = static_cast<const EntryPOD*>(d_entries);
+    DevBuf counts, cursor, scan, pos, ctmp, vtmp, misc;
+    if (counts.alloc((size_t)rows * 4) != cudaSuccess || cursor.alloc((size_t)rows * 4) != cudaSuccess ||
+        scan.alloc((size_t)rows * 8) != cudaSuccess || pos.alloc((size_t)nnz * 4) != cudaSuccess ||
+        ctmp.alloc((size_t)nnz * 4) != cudaSuccess || vtmp.alloc((size_t)nnz * 8) != cudaSuccess ||
+        misc.alloc(16) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200_ENOMEM, "coo_to_csr: cudaMalloc");
+    }
+    cudaMemsetAsync(counts.p, 0, (size_t)rows * 4, s);
+    cudaMemsetAsync(misc.p, 0, 16, s);
+    int* bad = misc.as<int>() + 2;
+    long long* total = misc.as<long long>();
+    int rc;
+    if (nnz > 0) {
+        coo_count_rows_kernel<<<gen_grid(nnz), 256, 0, s>>>(e, nnz, rows, counts.as<int>(), bad);
+        if ((rc = check_launch("coo_count_rows_kernel"))) return rc;
+    }
+    if ((rc = exclusive_scan<int>(counts.as<int>(), scan.as<long long>(), rows, total, s))) return rc;
+    int h_bad = 0;
+    cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (h_bad) return fail(B200_EINVAL, "coo_to_csr: entry with a row index outside [0, rows)");
+    coo_finish_row_ptr_kernel<<<gen_grid(rows + 1), 256, 0, s>>>(scan.as<long long>(), nnz, rows, d_row_ptr, cursor.as<int>());
+    if ((rc = check_launch("coo_finish_row_ptr_kernel"))) return rc;
+    if (nnz > 0) {
+        coo_scatter_kernel<<<gen_grid(nnz), 256, 0, s>>>(e, nnz, rows, cursor.as<int>(), d_col_idx, d_values, pos.as<int>());
+        if ((rc = check_launch("coo_scatter_kernel"))) return rc;
+        const long long warps = ((long long)rows + 31) / 32;
+        const long long blocks = (warps * 32 + 255) / 256;
+        csr_sort_rows_kernel<48><<<(unsigned)blocks, 256, 0, s>>>(d_row_ptr, rows, d_col_idx, d_values, pos.as<int>(),
+                                                               ctmp.as<int>(), vtmp.as<double>());
+        if ((rc = check_launch("csr_sort_rows_kernel"))) return rc;
+    }
+    cudaError_t err = cudaStreamSynchronize(s);  // temporaries are freed on return
+    if (err != cudaSuccess) return fail(B200_ECUDA, "coo_to_csr: %s", cudaGetErrorString(err));
+    return B200_OK;
+}
+
+extern "C" int b200_parse_mtx_entries(const void* d_text, long long n_bytes, long long max_entries, void* d_entries,
+                                      long long* n_lines_out, int* n_inexact_out, long long* h_inexact_pairs,
+                                      int inexact_cap, int* malformed_out, b200_stream stream) {
+    if (!d_text || n_bytes < 0 || !d_entries || !n_lines_out || !n_inexact_out || !malformed_out || inexact_cap < 0)
+        return fail(B200_EINVAL, "parse_mtx: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long chunks = (n_bytes + PARSE_CHUNK - 1) / PARSE_CHUNK;
+    DevBuf counts, first, misc, list;
+    if (counts.alloc((size_t)chunks * 4) != cudaSuccess || first.alloc((size_t)chunks * 8) != cudaSuccess ||
+        misc.alloc(32) != cudaSuccess || list.alloc((size_t)inexact_cap * 16) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200_ENOMEM, "parse_mtx: cudaMalloc");
+    }
+    cudaMemsetAsync(misc.p, 0, 32, s);
+    long long* total = misc.as<long long>();
+    int* n_inexact = misc.as<int>() + 2;
+    int* bad = misc.as<int>() + 3;
+    const unsigned char* t = static_cast<const unsigned char*>(d_text);
+    int rc;
+    if (chunks > 0) {
+        mtx_count_lines_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(t, n_bytes, counts.as<int>());
+        if ((rc = check_launch("mtx_count_lines_kernel"))) return rc;
+    }
+    if ((rc = exclusive_scan<int>(counts.as<int>(), first.as<long long>(), chunks, total, s))) return rc;
+    if (chunks > 0) {
+        mtx_parse_lines_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(
+            t, n_bytes, first.as<long long>(), max_entries, static_cast<EntryPOD*>(d_entries), n_inexact,
+            list.as<long long>(), inexact_cap, bad);
+        if ((rc = check_launch("mtx_parse_lines_kernel"))) return rc;
+    }
+    long long h_total = 0;
+    int h_misc[2] = {0, 0};
+    cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h_misc, n_inexact, 8, cudaMemcpyDeviceToHost, s);
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) return fail(B200_ECUDA, "parse_mtx: %s", cudaGetErrorString(err));
+    *n_lines_out = h_total;
+    *n_inexact_out = h_misc[0];
+    *malformed_out = h_misc[1];
+    const int ncopy = h_misc[0] < inexact_cap ? h_misc[0] : inexact_cap;
+    if (ncopy > 0 && h_inexact_pairs)
+        cudaMemcpy(h_inexact_pairs, list.p, (size_t)ncopy * 16, cudaMemcpyDeviceToHost);
+    return B200_OK;
 }

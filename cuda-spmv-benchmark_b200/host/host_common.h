@@ -82,4 +82,11 @@ MatrixData b200_synthetic_stencil(int grid_size);
 int b200_set_tuning(int variant, int rows_per_item);
 void b200_get_tuning(int* variant, int* rows_per_item);
 int b200_last_phase_times(double* ms9, int* count9);
+// device-resident ingest: .mtx -> COO on the GPU -> operator (no host Entry[] / CSR)
+int b200_load_matrix_market_device(const char* filename, MatrixData* meta, void** d_entries_out);
+int b200_operator_init_device_coo(SpmvOperator* op, const MatrixData* meta, const void* d_entries);
+int b200_operator_device_csr(SpmvOperator* op, const int** d_row_ptr, const int** d_col_idx, const double** d_values,
+                             long long* nnz);
+void b200_free_device(void* d_ptr);
+int b200_copy_to_host(void* h_dst, const void* d_src, size_t bytes);
 }

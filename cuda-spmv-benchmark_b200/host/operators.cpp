@@ -255,3 +255,53 @@ extern "C" SpmvOperator* get_operator(const char* mode) {
     if (!strcmp(mode, "stencil5-halo-mgpu")) return &SPMV_STENCIL_HALO_MGPU;
     return nullptr;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident ingest: initialise a CSR-based operator from COO entries that
+// already live on the GPU (e.g. parsed there by b200_load_matrix_market_device).  No host Entry[]
+// and no host CSR are built; csr_mat only carries the sizes.
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_operator_init_device_coo(SpmvOperator* op, const MatrixData* meta, const void* d_entries) {
+    OpState* st = (op == &SPMV_CSR) ? &g_csr : (op == &SPMV_STENCIL5_CSR) ? &g_st_csr : nullptr;
+    if (!st || !meta || (!d_entries && meta->nnz > 0) || meta->rows <= 0) {
+        fprintf(stderr, "[ERROR] b200_operator_init_device_coo: needs the cusparse-csr or stencil5-csr operator\n");
+        return EXIT_FAILURE;
+    }
+    if (st->kind == K_STENCIL_CSR) {
+        const long long n = meta->grid_size;
+        if (n < 1 || n * n != (long long)meta->rows) return EXIT_FAILURE;
+    }
+    st->reset();
+    st->rows = meta->rows; st->cols = meta->cols; st->ell_width = 0;
+    DeviceBand& b = st->band;
+    b.row_offset = 0; b.n_local = meta->rows; b.nnz_local = meta->nnz; b.values_len = (long long)meta->nnz + 2;
+    b.grid = meta->grid_size; b.layout = 0;
+    B200_CUDA(cudaMalloc(&b.d_row_ptr, ((size_t)meta->rows + 1) * sizeof(int)));
+    B200_CUDA(cudaMalloc(&b.d_col_idx, ((size_t)meta->nnz + 2) * sizeof(int)));
+    B200_CUDA(cudaMalloc(&b.d_values, ((size_t)meta->nnz + 2) * sizeof(double)));
+    B200_CUDA(cudaMemset(b.d_values + meta->nnz, 0, 2 * sizeof(double)));
+    int rc = b200_coo_to_csr(d_entries, meta->nnz, meta->rows, b.d_row_ptr, b.d_col_idx, b.d_values, 0);
+    if (rc) { fprintf(stderr, "[b200] %s\n", b200_last_error()); st->reset(); return EXIT_FAILURE; }
+    if (st->kind == K_CSR) {
+        rc = b200_csr_plan_build(b.d_row_ptr, meta->rows, meta->nnz, &st->plan, 0);
+        if (rc) { fprintf(stderr, "[b200] %s\n", b200_last_error()); st->reset(); return EXIT_FAILURE; }
+    }
+    B200_CUDA(cudaMalloc(&st->dX, (size_t)meta->cols * sizeof(double)));
+    B200_CUDA(cudaMalloc(&st->dY, (size_t)meta->rows * sizeof(double)));
+    B200_CUDA(cudaDeviceSynchronize());
+    csr_mat.nb_rows = meta->rows; csr_mat.nb_cols = meta->cols; csr_mat.nb_nonzeros = meta->nnz;
+    st->ready = true;
+    return EXIT_SUCCESS;
+}
+
+// copies of the operator's device CSR arrays (tests / debugging)
+extern "C" int b200_operator_device_csr(SpmvOperator* op, const int** d_row_ptr, const int** d_col_idx,
+                                        const double** d_values, long long* nnz) {
+    const DeviceBand* b = (op == &SPMV_CSR && g_csr.ready) ? &g_csr.band : operator_band(op);
+    if (!b) return 1;
+    if (d_row_ptr) *d_row_ptr = b->d_row_ptr;
+    if (d_col_idx) *d_col_idx = b->d_col_idx;
+    if (d_values) *d_values = b->d_values;
+    if (nnz) *nnz = b->nnz_local;
+    return 0;
+}

@@ -104,6 +104,7 @@ C_SYMBOLS = [
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
+    "b200_coo_to_csr", "b200_parse_mtx_entries",
     # include/b200/api.h, extern "C" part
     "csr_mat", "ellpack_matrix", "build_ellpack_from_csr_local", "ensure_ellpack_structure_built", "get_operator",
     "calculate_spmv_metrics", "get_gpu_properties", "print_benchmark_metrics", "print_metrics_json",
@@ -114,7 +115,8 @@ C_SYMBOLS = [
     # extensions (host/host_common.h)
     "b200_operator_band", "b200_mgpu_init_single_process", "b200_mgpu_init_rank", "b200_mgpu_connect",
     "b200_mgpu_world", "b200_mgpu_rank", "b200_mgpu_finalize", "b200_synthetic_stencil", "b200_set_tuning",
-    "b200_get_tuning", "b200_last_phase_times",
+    "b200_get_tuning", "b200_last_phase_times", "b200_load_matrix_market_device", "b200_operator_init_device_coo",
+    "b200_operator_device_csr", "b200_free_device", "b200_copy_to_host",
 ]
 # C++-linkage symbols of the reference API (Itanium mangling)
 CXX_SYMBOLS = {
@@ -180,6 +182,8 @@ def load():
     L.b200_gen_stencil5_ellpack.argtypes = [i32, ll, ll, dbl, dbl, vp, vp, vp]
     L.b200_gen_stencil5_entries.argtypes = [i32, ll, ll, dbl, dbl, vp, vp]
     L.b200_fill.argtypes = [vp, ll, dbl, vp]
+    L.b200_coo_to_csr.argtypes = [vp, ll, i32, vp, vp, vp, vp]
+    L.b200_parse_mtx_entries.argtypes = [vp, ll, ll, vp, C.POINTER(ll), C.POINTER(i32), vp, i32, C.POINTER(i32), vp]
     # host API
     L.get_operator.restype = C.POINTER(SpmvOperator)
     L.get_operator.argtypes = [C.c_char_p]
@@ -209,6 +213,12 @@ def load():
     L.b200_synthetic_stencil.argtypes = [i32]
     L.b200_set_tuning.argtypes = [i32, i32]
     L.b200_last_phase_times.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
+    L.b200_load_matrix_market_device.argtypes = [C.c_char_p, C.POINTER(MatrixData), C.POINTER(vp)]
+    L.b200_operator_init_device_coo.argtypes = [C.POINTER(SpmvOperator), C.POINTER(MatrixData), vp]
+    L.b200_operator_device_csr.argtypes = [C.POINTER(SpmvOperator), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
+    L.b200_free_device.argtypes = [vp]
+    L.b200_free_device.restype = None
+    L.b200_copy_to_host.argtypes = [vp, vp, C.c_size_t]
     # C++-linkage entry points
     L.build_csr_struct = getattr(L, CXX_SYMBOLS["build_csr_struct"])
     L.build_csr_struct.argtypes = [C.POINTER(MatrixData)]

@@ -183,6 +183,21 @@ int b200_gen_stencil5_entries(int grid_size, long long row_offset, long long n_l
                               double neighbour, void* d_entries, b200_stream stream);
 int b200_fill(double* d_p, long long n, double value, b200_stream stream);
 
+/* ---- device-side ingest (arbitrary matrices) -----------------------------------------------
+ * COO -> CSR on the device, bit-identical to build_csr_struct (src/spmv/spmv_cusparse_csr.cu:85-157):
+ * rows ascending, columns ascending inside a row, equal columns in input order.  d_entries is an
+ * array of {int row; int col; double value;} (0-based).  d_row_ptr: rows+1 ints. */
+int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int* d_row_ptr, int* d_col_idx,
+                    double* d_values, b200_stream stream);
+/* Parses the ENTRY lines of a Matrix Market file ("i j value", 1-based) held in device memory into
+ * d_entries (0-based), like the fscanf loop of src/io/io.cu:153-166.  n_lines_out = non-blank lines
+ * found; literals outside the exact fast path are listed as (entry index, byte offset of the value
+ * token) pairs in h_inexact_pairs for the caller to redo with strtod; malformed_out != 0 when a
+ * line does not hold exactly three tokens (caller should use the host reader). */
+int b200_parse_mtx_entries(const void* d_text, long long n_bytes, long long max_entries, void* d_entries,
+                           long long* n_lines_out, int* n_inexact_out, long long* h_inexact_pairs,
+                           int inexact_cap, int* malformed_out, b200_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
