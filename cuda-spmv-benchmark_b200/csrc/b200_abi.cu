@@ -231,17 +231,110 @@ extern "C" int b200_spmv_stencil5_halo(const int* d_row_ptr, const int* d_col_id
 // generic CSR / ELLPACK
 // ------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kCsrWarps = 8;
+constexpr int kCsrWarps = 8;  // legacy warp-stream kernel (variant 100), kept for A/B measurements
 
-int launch_csr(const CsrArgs& a, cudaStream_t s) {
-    if (a.n_rows == 0) return B200_OK;
+struct CsrVariant {
+    int warps, stages, win;
+    const char* info;
+};
+// keep in sync with the dispatch switch in launch_csr
+const CsrVariant kCsrVariants[] = {
+    {8, 8, 128, "c0 (default): 8 warps/CTA, ring of 8 x 128-entry windows, 2 CTAs/SM"},
+    {4, 8, 128, "c1: 4 warps/CTA, ring of 8 x 128-entry windows, 4 CTAs/SM"},
+    {8, 4, 256, "c2: 8 warps/CTA, ring of 4 x 256-entry windows, 2 CTAs/SM"},
+    {4, 4, 256, "c3: 4 warps/CTA, ring of 4 x 256-entry windows, 4 CTAs/SM"},
+    {8, 8, 64, "c4: 8 warps/CTA, ring of 8 x 64-entry windows, 3 CTAs/SM"},
+    {8, 4, 128, "c5: 8 warps/CTA, ring of 4 x 128-entry windows, 3 CTAs/SM"},
+    {8, 8, 64, "c6: 8 warps/CTA, ring of 8 x 64-entry windows, 4 CTAs/SM"},
+    {8, 4, 128, "c7: 8 warps/CTA, ring of 4 x 128-entry windows, 4 CTAs/SM"},
+};
+const int kNumCsrVariants = (int)(sizeof(kCsrVariants) / sizeof(kCsrVariants[0]));
+
+std::atomic<int> g_csr_default_variant{0};
+int csr_default_variant() { return g_csr_default_variant.load(std::memory_order_relaxed); }
+constexpr int kCsrGroupsPerItem = 32;  // 1024 rows per warp item
+
+template <int WARPS, int STAGES, int WIN, bool ELL, int MINB>
+int launch_csr_ring(const CsrArgs& a, int gpw_override, cudaStream_t s) {
+    auto k = csr_ring_kernel<WARPS, STAGES, WIN, ELL, MINB>;
+    const size_t smem = (size_t)WARPS * csr_ring_warp_bytes<STAGES, WIN>();
+    static int resident_ctas = 0;  // per instantiation: CTAs that fit the whole GPU at once
+    if (resident_ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0, dev = 0, n_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, WARPS * 32, smem);
+        if (e == cudaSuccess) e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || occ < 1 || n_sm < 1) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "csr: kernel setup: %s", cudaGetErrorString(e));
+            return (e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction ||
+                    e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+                       ? B200_ENODEV
+                       : B200_ECUDA;
+        }
+        resident_ctas = occ * n_sm;
+    }
+    // one item (run of 32-row groups) per warp, handed out in launch order; small matrices get
+    // shorter items so that every SM has work
+    const long long groups = (a.n_rows + 31) / 32;
+    const long long resident_warps = (long long)resident_ctas * WARPS;
+    long long gpw = gpw_override > 0 ? gpw_override : kCsrGroupsPerItem;
+    if (gpw_override <= 0 && groups < 4 * resident_warps * gpw) {
+        gpw = groups / (4 * resident_warps);
+        if (gpw < 1) gpw = 1;
+    }
+    const long long warps = (groups + gpw - 1) / gpw;
+    const long long blocks = (warps + WARPS - 1) / WARPS;
+    if (blocks > 2147483647LL) return fail(B200_EINVAL, "csr: too many row blocks");
+    k<<<(unsigned)blocks, WARPS * 32, smem, s>>>(a, (int)gpw);
+    return check_launch("csr_ring_kernel");
+}
+
+template <bool ELL>
+int launch_csr_variant(int v, int gpw, const CsrArgs& a, cudaStream_t s) {
+    switch (v) {
+        case 1: return launch_csr_ring<4, 8, 128, ELL, 4>(a, gpw, s);
+        case 2: return launch_csr_ring<8, 4, 256, ELL, 2>(a, gpw, s);
+        case 3: return launch_csr_ring<4, 4, 256, ELL, 4>(a, gpw, s);
+        case 4: return launch_csr_ring<8, 8, 64, ELL, 3>(a, gpw, s);
+        case 5: return launch_csr_ring<8, 4, 128, ELL, 3>(a, gpw, s);
+        case 6: return launch_csr_ring<8, 8, 64, ELL, 4>(a, gpw, s);
+        case 7: return launch_csr_ring<8, 4, 128, ELL, 4>(a, gpw, s);
+        default: return launch_csr_ring<8, 8, 128, ELL, 2>(a, gpw, s);
+    }
+}
+
+int launch_csr_legacy(const CsrArgs& a, cudaStream_t s) {
     const long long rows_per_cta = 32LL * kCsrWarps;
     const long long blocks = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
     if (blocks > 2147483647LL) return fail(B200_EINVAL, "csr: too many row blocks");
     csr_warp_stream_kernel<kCsrWarps><<<(unsigned)blocks, kCsrWarps * 32, 0, s>>>(a);
     return check_launch("csr_warp_stream_kernel");
 }
+
+// variant = tuning variant + 1000 * (groups per item override); 100 = legacy warp-stream kernel
+int launch_csr(const CsrArgs& a, int variant, cudaStream_t s) {
+    if (a.n_rows == 0) return B200_OK;
+    if (a.n_rows < 0) return fail(B200_EINVAL, "csr: negative row count");
+    if (variant <= 0) variant = csr_default_variant();
+    const int gpw = variant / 1000;
+    variant %= 1000;
+    // the bulk copies need 16-byte aligned arrays; anything else takes the register-staged kernel
+    const bool aligned = (((uintptr_t)a.col_idx | (uintptr_t)a.values | (uintptr_t)a.row_ptr) & 15) == 0;
+    if (variant == 100 || !aligned) return launch_csr_legacy(a, s);
+    if (variant >= kNumCsrVariants) variant = 0;
+    return a.row_ptr ? launch_csr_variant<false>(variant, gpw, a, s) : launch_csr_variant<true>(variant, gpw, a, s);
+}
 }  // namespace
+
+extern "C" void b200_csr_set_default_variant(int v) {
+    g_csr_default_variant.store(v > 0 ? v : 0, std::memory_order_relaxed);
+}
+
+extern "C" const char* b200_csr_variant_info(int v) {
+    return (v >= 0 && v < kNumCsrVariants) ? kCsrVariants[v].info : nullptr;
+}
 
 extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long long nnz, b200_csr_plan* plan,
                                    b200_stream stream) {
@@ -266,15 +359,18 @@ extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long 
     memcpy(plan->hist, h, 33 * sizeof(unsigned long long));
     plan->max_row_len = h[33];
     plan->mean_row_len = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
-    // Long-row threshold from the histogram: 32-row groups whose mean row length exceeds it are
-    // processed warp-per-row, everything else by the bit-exact stream path.  A matrix dominated by
-    // long rows (median bin above 64 entries) gets a lower threshold so that its groups vectorise.
+    // Scheme pick from the histogram.  Every 32-row group decides at run time between lane-per-row
+    // (bit-exact k order, x gathered one group ahead) and warp-per-row; the histogram sets the row
+    // length above which a group goes warp-per-row: matrices whose MEDIAN row is longer than 16
+    // entries (bin 5 and up) switch early, because lane-per-row walks entries past its 8-deep x
+    // prefetch serially, while for short-row matrices an occasional 17..32-entry row is cheaper to
+    // finish in place than to hand the whole group to the warp-per-row path.
     unsigned long long acc = 0, half = (unsigned long long)(0.5 * (double)n_rows);
     int median_bin = 0;
     for (int b = 0; b < 33; b++) { acc += h[b]; if (acc >= half) { median_bin = b; break; } }
-    plan->rows_per_block = 32 * kCsrWarps;
-    plan->window = 256;
-    plan->vector_threshold = (median_bin > 6) ? 48 : 96;
+    plan->rows_per_block = 32 * kCsrGroupsPerItem;
+    plan->window = kCsrVariants[0].win;
+    plan->vector_threshold = (median_bin >= 5) ? 16 : 32;
     return B200_OK;
 }
 
@@ -284,9 +380,9 @@ extern "C" int b200_spmv_csr(const b200_csr_plan* plan, const int* d_row_ptr, co
     if (!plan || !d_row_ptr || !d_x || !d_y) return fail(B200_EINVAL, "csr: NULL argument");
     CsrArgs a;
     a.row_ptr = d_row_ptr; a.col_idx = d_col_idx; a.values = d_values; a.x = d_x; a.y = d_y;
-    a.n_rows = n_rows; a.ell_width = 0; a.vector_threshold = plan->vector_threshold > 0 ? plan->vector_threshold : 96;
+    a.n_rows = n_rows; a.ell_width = 0; a.vector_threshold = plan->vector_threshold > 0 ? plan->vector_threshold : 32;
     a.alpha = alpha; a.beta = beta;
-    return launch_csr(a, (cudaStream_t)stream);
+    return launch_csr(a, plan->variant, (cudaStream_t)stream);
 }
 
 extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
@@ -297,7 +393,7 @@ extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, c
     a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
     a.n_rows = n_rows; a.ell_width = width; a.vector_threshold = 1 << 20;  // ELLPACK rows are uniform: always stream
     a.alpha = alpha; a.beta = beta;
-    return launch_csr(a, (cudaStream_t)stream);
+    return launch_csr(a, 0, (cudaStream_t)stream);
 }
 
 extern "C" int b200_spmv_stencil5_ellpack(const double* d_values, const int* d_col_indices, const double* d_x,

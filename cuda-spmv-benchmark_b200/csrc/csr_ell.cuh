@@ -136,4 +136,341 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
     }
 }
 
+
+// ================================================================================================
+// csr_ring_kernel -- the production CSR / ELLPACK kernel ("warp ring").
+//
+// A WARP owns one item = `groups_per_warp` consecutive 32-row groups, i.e. one contiguous range
+// [K0, K1) of col_idx / values.  Items are handed out in launch order, so the resident warps form
+// a wavefront over the matrix and banded x accesses of neighbouring items hit in L2.
+//   * Lane 0 streams the range in fixed windows of WIN entries into a warp-private circular
+//     shared-memory buffer of STAGES windows with 1-D bulk async copies (TMA engine, SASS UBLKCP;
+//     mbarrier complete_tx, L2 evict-first): independent of where rows begin, no registers tied
+//     up, up to STAGES-1 windows in flight per warp.  row_ptr travels the same way through a small
+//     second ring (chunks of 128 rows).
+//   * Short rows ("lane per row", groups with at most RING/2 - WIN entries and rows no longer than
+//     `vector_threshold`): every lane owns one row of the group.  One group AHEAD of the
+//     arithmetic it reads its first 8 column ids from shared memory and launches the x gathers
+//     into registers, so the gather latency hides behind the previous group's work; then
+//     sum = fma(v[k], x[col[k]], sum) for k ascending -- bit-identical to the scalar reference.
+//   * Long rows ("warp per row"): lanes stride over the row, lane l takes the entries with
+//     (k - row_start) % 32 == l in k order, butterfly sum at the row end (rounding-level
+//     difference to the sequential order, documented tolerance 1e-12).  Rows may be longer than
+//     the ring: they stream through it window by window.
+// Only __syncwarp is used; warps are fully independent.  All three arrays must be 16-byte aligned
+// (the launcher routes anything else to csr_warp_stream_kernel above).
+// ================================================================================================
+constexpr int kCsrRpChunk = 128;  // rows per row_ptr ring slot (4 groups)
+constexpr int kCsrRpSlot = kCsrRpChunk + 8;
+constexpr int kCsrPrefetch = 8;  // x values per row gathered one group ahead
+constexpr int kCsrMirror = 32;   // ring[0, 32) is mirrored behind the ring end: a lane-per-row row
+                                 // (at most 32 entries) never wraps, its shared addresses are base + j
+
+// lane-per-row step 1: column ids of the lane's first N entries -> x gathers in flight.  The loads are
+// unconditional (slots past the row end read x[0]) so that they compile to straight-line code.
+template <int N, bool ELL>
+__device__ __forceinline__ void lpr_gather(const int* __restrict__ pc, int len, const double* __restrict__ x,
+                                           double (&xq)[kCsrPrefetch], uint32_t& pm) {
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        int c = (j < len) ? pc[j] : 0;
+        if (ELL) {
+            pm |= (c >= 0 ? 1u : 0u) << j;
+            c = max(c, 0);
+        }
+        xq[j] = __ldg(x + c);
+    }
+}
+// lane-per-row step 2: the k-ordered fma chain over the first N entries
+template <int N, bool ELL>
+__device__ __forceinline__ double lpr_chain(const double* __restrict__ pv, int len, const double (&xq)[kCsrPrefetch],
+                                            uint32_t pm) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (j < len && (!ELL || ((pm >> j) & 1u))) sum = fma(pv[j], xq[j], sum);
+    return sum;
+}
+#define B200_CSR_DISPATCH_N(n, CALL)                                                              \
+    switch (n) {                                                                                  \
+        case 0: break;                                                                            \
+        case 1: { constexpr int N_ = 1; CALL; } break;                                            \
+        case 2: { constexpr int N_ = 2; CALL; } break;                                            \
+        case 3: { constexpr int N_ = 3; CALL; } break;                                            \
+        case 4: { constexpr int N_ = 4; CALL; } break;                                            \
+        case 5: { constexpr int N_ = 5; CALL; } break;                                            \
+        case 6: { constexpr int N_ = 6; CALL; } break;                                            \
+        case 7: { constexpr int N_ = 7; CALL; } break;                                            \
+        default: { constexpr int N_ = 8; CALL; } break;                                           \
+    }
+
+template <int STAGES, int WIN>
+__host__ __device__ constexpr size_t csr_ring_warp_bytes() {
+    return (size_t)(STAGES * WIN + kCsrMirror) * 12  // values + column ring (+ wrap mirror)
+           + (size_t)2 * kCsrRpSlot * 4         // row_ptr ring
+           + (size_t)(STAGES + 2) * 8;          // mbarriers
+}
+
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+struct CsrGroup {
+    int s, len;            // per lane: local start of its row, row length
+    int gs, nnz, maxlen;   // uniform: local start of the group, its entries, longest row
+    bool lpr;              // uniform: lane-per-row (else warp-per-row)
+};
+
+template <int WARPS, int STAGES, int WIN, bool ELL, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArgs a, const int groups_per_warp) {
+    constexpr int RING = STAGES * WIN, M = RING - 1, J = kCsrPrefetch;
+    constexpr int LIMIT = RING - 2 * WIN;  // a lane-per-row group must fit the ring beside one window in flight
+    constexpr int RC = kCsrRpChunk, RSLOT = kCsrRpSlot;
+    static_assert((RING & M) == 0 && (STAGES & (STAGES - 1)) == 0, "ring sizes must be powers of two");
+    static_assert(LIMIT >= 32, "ring too small");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    const long long Ra = ((long long)blockIdx.x * WARPS + warp) * groups_per_warp * 32;
+    if (Ra >= a.n_rows) return;
+    const int nrows = (int)min((long long)groups_per_warp * 32, a.n_rows - Ra);
+    const int ngroups = (nrows + 31) >> 5;
+
+    unsigned char* wbase = smem_raw + (size_t)warp * csr_ring_warp_bytes<STAGES, WIN>();
+    double* sval = reinterpret_cast<double*>(wbase);
+    int* scol = reinterpret_cast<int*>(sval + RING + kCsrMirror);
+    int* srp = scol + RING + kCsrMirror;
+    const uint32_t sval_a = smem_u32(sval), scol_a = smem_u32(scol), srp_a = smem_u32(srp);
+    const uint32_t bar_a = smem_u32(srp + 2 * RSLOT);  // [0,STAGES) windows, then 2 row_ptr slots
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES + 2; i++) mbar_init(reinterpret_cast<uint64_t*>(srp + 2 * RSLOT) + i, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const uint64_t policy = l2_policy_evict_first();
+    const double* __restrict__ xp = a.x;
+
+    // ---------------------------------------------------------------- row_ptr ring (CSR only)
+    const int n_chunks = (nrows + RC - 1) / RC;
+    const long long rp_t4 = ((a.n_rows + 1) & ~3LL) - Ra;  // bulk-copyable row_ptr entries, item-local
+    auto issue_rp = [&](int c) {
+        const long long left = rp_t4 - (long long)c * RC;
+        const int cnt = left < RC + 4 ? (int)left : RC + 4;
+        if (lane == 0 && cnt > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bar = bar_a + (STAGES + (c & 1)) * 8;
+            mbar_expect_tx_a(bar, cnt * 4);
+            bulk_g2s_a(srp_a + (c & 1) * RSLOT * 4, a.row_ptr + Ra + (long long)c * RC, cnt * 4, bar, policy);
+        }
+    };
+    auto wait_rp = [&](int c) {
+        const long long left = rp_t4 - (long long)c * RC;
+        if (left > 0) mbar_wait_a(bar_a + (STAGES + (c & 1)) * 8, (c >> 1) & 1);
+        if (left < RC + 1) {  // tail of row_ptr the 16-byte granularity could not cover (last chunk only)
+            const int lo = left > 0 ? (int)left : 0;
+            const int hi = min(RC, nrows - c * RC) + 1;
+            int* dst = srp + (c & 1) * RSLOT;
+            for (int k = lo + lane; k < hi; k += 32) dst[k] = a.row_ptr[Ra + (long long)c * RC + k];
+        }
+        __syncwarp();
+    };
+
+    long long K0, K1, total;
+    if (ELL) {
+        K0 = Ra * a.ell_width;
+        K1 = (Ra + nrows) * a.ell_width;
+        total = a.n_rows * a.ell_width;
+    } else {
+        issue_rp(0);
+        long long t = 0;
+        if (lane == 0) t = a.row_ptr[Ra];
+        if (lane == 1) t = a.row_ptr[Ra + nrows];
+        if (lane == 2) t = a.row_ptr[a.n_rows];
+        K0 = __shfl_sync(B200_FULL, t, 0);
+        K1 = __shfl_sync(B200_FULL, t, 1);
+        total = __shfl_sync(B200_FULL, t, 2);
+    }
+    // item-local entry index = absolute index - wk0 (wk0 16-byte aligned for both arrays)
+    const long long wk0 = K0 & ~3LL;
+    const int k0l = (int)(K0 - wk0), k1l = (int)(K1 - wk0);
+    const long long t4 = (total & ~3LL) - wk0, tt = total - wk0;
+    const int tl4 = t4 > 0x7fffff00LL ? 0x7fffff00 : (int)t4;   // bulk-copyable entries
+    const int totl = tt > 0x7fffff00LL ? 0x7fffff00 : (int)tt;  // readable entries
+    const int nwin = (k1l > k0l) ? (k1l + WIN - 1) / WIN : 0;
+    const int* colp = a.col_idx + wk0;
+    const double* valp = a.values + wk0;
+    const int wk0i = (int)wk0;  // CSR: absolute entry indices are ints
+
+    // ---------------------------------------------------------------- window ring
+    int issued = 0, landed = 0, landed_end = 0, released_end = WIN;  // landed_end = landed * WIN
+    auto issue_window = [&](int j) {
+        const int cnt = min(WIN, tl4 - j * WIN);
+        if (lane == 0 && cnt > 0) {
+            // order the slot's earlier generic-proxy reads before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const int slot = j & (STAGES - 1);
+            const uint32_t bar = bar_a + slot * 8;
+            mbar_expect_tx_a(bar, cnt * 12);
+            bulk_g2s_a(sval_a + slot * WIN * 8, valp + (size_t)j * WIN, cnt * 8, bar, policy);
+            bulk_g2s_a(scol_a + slot * WIN * 4, colp + (size_t)j * WIN, cnt * 4, bar, policy);
+        }
+    };
+    // make entries [0, kend) available in the ring
+    auto ensure = [&](int kend) {
+        while (landed_end < kend) {
+            const int j = landed;
+            if (tl4 > j * WIN) mbar_wait_a(bar_a + (j & (STAGES - 1)) * 8, (j / STAGES) & 1);
+            if ((j + 1) * WIN > tl4) {  // array tail outside the 16-byte granules (matrix end only)
+                const int lo = max(tl4, j * WIN), hi = min(totl, (j + 1) * WIN);
+                for (int k = lo + lane; k < hi; k += 32) {
+                    sval[k & M] = valp[k];
+                    scol[k & M] = colp[k];
+                }
+                __syncwarp();
+            }
+            if ((j & (STAGES - 1)) == 0) {  // refresh the wrap mirror
+                sval[RING + lane] = sval[lane];
+                scol[RING + lane] = scol[lane];
+                __syncwarp();
+            }
+            landed++;
+            landed_end += WIN;
+        }
+    };
+    // entries below k are dead: recycle their windows
+    auto release = [&](int k) {
+        while (released_end <= k) {
+            __syncwarp();
+            released_end += WIN;
+            if (issued < nwin) issue_window(issued++);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < STAGES; i++)
+        if (issued < nwin) issue_window(issued++);
+
+    // ---------------------------------------------------------------- groups
+    int cur_chunk = -1;
+    auto load_group = [&](int gi, CsrGroup& G) {
+        const int r0 = min(gi * 32 + lane, nrows), r1 = min(gi * 32 + lane + 1, nrows);
+        int e;
+        if (ELL) {
+            G.s = k0l + r0 * a.ell_width;
+            e = k0l + r1 * a.ell_width;
+        } else {
+            const int c = min(gi / (RC / 32), n_chunks - 1);  // gi >= ngroups: empty sentinel group
+            if (c != cur_chunk) {
+                __syncwarp();
+                if (c + 1 < n_chunks) issue_rp(c + 1);  // into the slot of chunk c-1: every lane is done with it
+                wait_rp(c);
+                cur_chunk = c;
+            }
+            const int* rp = srp + (c & 1) * RSLOT - c * RC;
+            G.s = rp[r0] - wk0i;
+            e = rp[r1] - wk0i;
+        }
+        G.len = e - G.s;
+        G.gs = __shfl_sync(B200_FULL, G.s, 0);
+        G.nnz = __shfl_sync(B200_FULL, e, 31) - G.gs;
+        G.maxlen = __reduce_max_sync(B200_FULL, G.len);
+        G.lpr = G.nnz <= LIMIT && G.maxlen <= min(a.vector_threshold, kCsrMirror);
+    };
+    // lane-per-row, step 1 (one group ahead): column ids -> x gathers in flight
+    auto prefetch = [&](const CsrGroup& G, double (&xq)[J], uint32_t& pm) {
+        pm = 0;
+        const int* pc = scol + (G.s & M);
+        B200_CSR_DISPATCH_N(G.maxlen, (lpr_gather<N_, ELL>(pc, G.len, xp, xq, pm)));
+    };
+    // lane-per-row, step 2: the k-ordered fma chain of this lane's row
+    auto process_lpr = [&](const CsrGroup& G, const double (&xq)[J], uint32_t pm) {
+        double sum = 0.0;
+        const double* pv = sval + (G.s & M);
+        B200_CSR_DISPATCH_N(G.maxlen, (sum = lpr_chain<N_, ELL>(pv, G.len, xq, pm)));
+        if (G.maxlen > J) {  // rows longer than the prefetch depth
+            const int* pc = scol + (G.s & M);
+            for (int j = J; j < G.maxlen; j++) {
+                if (j < G.len) {
+                    const int c = pc[j];
+                    if (!ELL || c >= 0) sum = fma(pv[j], __ldg(xp + c), sum);
+                }
+            }
+        }
+        return sum;
+    };
+    // warp-per-row: the rows of the group one after the other, streamed through the ring
+    auto process_vec = [&](const CsrGroup& G, int rows_here) {
+        double sum = 0.0;
+        for (int q = 0; q < rows_here; q++) {
+            const int qs = __shfl_sync(B200_FULL, G.s, q);
+            const int qe = qs + __shfl_sync(B200_FULL, G.len, q);
+            double part = 0.0;
+            int k = qs;
+            while (k < qe) {
+                const int ce = min(qe, (k / WIN + 1) * WIN);  // stay inside one window
+                release(k);
+                ensure(ce);
+                for (int kk = k + ((lane - (k - qs)) & 31); kk < ce; kk += 32) {
+                    const int c = scol[kk & M];
+                    if (!ELL || c >= 0) part = fma(sval[kk & M], __ldg(xp + c), part);
+                }
+                k = ce;
+            }
+            part = warp_sum(part);
+            if (lane == q) sum = part;
+        }
+        return sum;
+    };
+
+    // Software pipeline over the groups (one copy of the code, one set of x registers):
+    //   chain(cur) -> y -> recycle windows below nxt -> gather(nxt) into the registers just freed
+    //   -> row extents of the group after nxt.
+    // The x gathers of `nxt` are in flight while everything behind them runs; behind the last group
+    // come empty sentinel groups, so there is no "has next" case.
+    double xq[J];
+    uint32_t pm = 0;
+    CsrGroup cur, nxt;
+    double* yp = a.y + Ra + lane;
+    const double alpha = a.alpha, beta = a.beta;
+    cur.lpr = true; cur.s = cur.len = cur.gs = cur.nnz = cur.maxlen = 0;
+    nxt = cur;
+    for (int gi = -2; gi < ngroups; gi++) {  // two warm-up turns fill the pipeline through the same code
+        if (gi >= 0) {
+            const double sum = cur.lpr ? process_lpr(cur, xq, pm) : process_vec(cur, min(32, nrows - gi * 32));
+            if (gi * 32 + lane < nrows) {
+                if (beta == 0.0) *yp = alpha * sum;
+                else *yp = fma(alpha, sum, beta * *yp);
+            }
+            yp += 32;
+        }
+        if (gi >= -1) {
+            release(nxt.gs);
+            if (nxt.lpr) {
+                ensure(nxt.gs + nxt.nnz);
+                prefetch(nxt, xq, pm);
+            }
+        }
+        cur = nxt;
+        load_group(gi + 2, nxt);
+    }
+}
+
 }  // namespace b200

@@ -88,7 +88,7 @@ class Band(C.Structure):  # b200_band, include/b200_kernels.h
 
 class CsrPlan(C.Structure):
     _fields_ = [("rows_per_block", C.c_int), ("window", C.c_int), ("vector_threshold", C.c_int),
-                ("reserved", C.c_int), ("hist", C.c_ulonglong * 33),
+                ("variant", C.c_int), ("hist", C.c_ulonglong * 33),
                 ("max_row_len", C.c_ulonglong), ("mean_row_len", C.c_double)]
 
 
@@ -97,7 +97,7 @@ C_SYMBOLS = [
     # include/b200_kernels.h
     "b200_version", "b200_last_error", "b200_launch_count", "b200_stencil5_spmv", "b200_spmv_stencil5_csr",
     "b200_spmv_stencil5_halo", "b200_spmv_stencil5_ellpack", "b200_stencil5_num_partials",
-    "b200_stencil5_variant_info", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
+    "b200_stencil5_variant_info", "b200_csr_variant_info", "b200_csr_set_default_variant", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push",
@@ -159,6 +159,10 @@ def load():
     L.b200_stencil5_num_partials.argtypes = [C.POINTER(Band)]
     L.b200_stencil5_variant_info.restype = C.c_char_p
     L.b200_stencil5_variant_info.argtypes = [i32]
+    L.b200_csr_variant_info.restype = C.c_char_p
+    L.b200_csr_variant_info.argtypes = [i32]
+    L.b200_csr_set_default_variant.restype = None
+    L.b200_csr_set_default_variant.argtypes = [i32]
     L.b200_csr_plan_build.argtypes = [vp, ll, ll, C.POINTER(CsrPlan), vp]
     L.b200_spmv_csr.argtypes = [C.POINTER(CsrPlan), vp, vp, vp, vp, vp, ll, dbl, dbl, vp]
     L.b200_spmv_ellpack.argtypes = [vp, vp, vp, vp, ll, i32, dbl, dbl, vp]

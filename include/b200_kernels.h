@@ -95,12 +95,16 @@ typedef struct {
     int rows_per_block;       /* rows per CTA (32 per warp) */
     int window;               /* shared-memory window per warp, in non-zeros */
     int vector_threshold;     /* mean row length of a 32-row group above which it runs warp-per-row */
-    int reserved;
+    int variant;              /* tuning variant (0 = default), see b200_csr_variant_info */
     unsigned long long hist[33]; /* rows with length in (2^(b-1), 2^b] */
     unsigned long long max_row_len;
     double mean_row_len;
 } b200_csr_plan;
 
+/* human-readable description of CSR tuning variant v (NULL past the last one) */
+const char* b200_csr_variant_info(int v);
+/* variant used when a plan says 0, and by b200_spmv_ellpack (tuning knob for tools/sweep.py) */
+void b200_csr_set_default_variant(int v);
 /* takes the row-length histogram on the device and picks the block shape */
 int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long long nnz, b200_csr_plan* plan,
                         b200_stream stream);

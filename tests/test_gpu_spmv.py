@@ -159,13 +159,26 @@ def random_csr(rng, rows, cols, lens):
     return a
 
 
-@pytest.mark.parametrize("kind", ["uniform5", "unbalanced", "empty_rows", "long_rows", "single"])
-def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind):
-    """row-length variety of tests/helpers/matrix_fixtures.cpp:296-370 (random_sparse, unbalanced_rows)"""
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 100])
+@pytest.mark.parametrize("kind", ["uniform5", "unbalanced", "empty_rows", "long_rows", "single", "mixed_tail"])
+def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind, variant):
+    """row-length variety of tests/helpers/matrix_fixtures.cpp:296-370 (random_sparse, unbalanced_rows),
+    through every tuning variant of the warp-ring kernel (and the legacy warp-stream kernel, 100)"""
     torch = torch_cuda
     L = B.load()
+    if variant not in (0, 100) and L.b200_csr_variant_info(variant) is None:
+        pytest.skip("no such variant")
+    L.b200_csr_set_default_variant(variant)
+    try:
+        _generic_csr_and_ellpack(B, orc, torch, L, kind, variant)
+    finally:
+        L.b200_csr_set_default_variant(0)
+
+
+def _generic_csr_and_ellpack(B, orc, torch, L, kind, variant):
     rng = np.random.default_rng(42)
-    rows = {"uniform5": 3000, "unbalanced": 2000, "empty_rows": 1500, "long_rows": 300, "single": 1}[kind]
+    rows = {"uniform5": 3000, "unbalanced": 2000, "empty_rows": 1500, "long_rows": 300, "single": 1,
+            "mixed_tail": 1237}[kind]
     cols = rows if kind != "long_rows" else 6000
     if kind == "uniform5":
         lens = np.full(rows, 5)
@@ -175,6 +188,10 @@ def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind):
         lens = np.where(rng.random(rows) < 0.5, 0, rng.integers(1, 9, rows))
     elif kind == "long_rows":
         lens = rng.integers(3000, 5000, rows)
+    elif kind == "mixed_tail":  # short rows, a run of long rows, empty rows at the very end
+        lens = rng.integers(0, 12, rows)
+        lens[400:470] = rng.integers(200, 900, 70)
+        lens[-40:] = 0
     else:
         lens = np.array([1])
     ent = random_csr(rng, rows, cols, lens)
@@ -190,10 +207,13 @@ def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind):
     plan = B.CsrPlan()
     B.check(L.b200_csr_plan_build(dptr(rp), rows, len(ova), C.byref(plan), None), "plan")
     assert sum(plan.hist) == rows and plan.max_row_len == lens.max()
+    plan.variant = variant
     B.check(L.b200_spmv_csr(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x), dptr(y), rows, 1.0, 0.0, None), "csr")
     torch.cuda.synchronize()
     yd = y.cpu().numpy()
-    if kind == "long_rows":  # groups of long rows go warp-per-row: different summation order
+    # groups with long rows go warp-per-row: different summation order, BASELINE tolerance 1e-12
+    loose = kind in ("unbalanced", "long_rows", "mixed_tail")
+    if loose:
         assert np.linalg.norm(yd - yo) / np.linalg.norm(yo) < 1e-12
     else:
         assert np.array_equal(yd, yo)
@@ -210,9 +230,56 @@ def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind):
         B.check(L.b200_spmv_ellpack(dptr(idx), dptr(val), dptr(x), dptr(y3), rows, w, 1.0, 0.0, None), "ell")
         torch.cuda.synchronize()
         y3h = y3.cpu().numpy()
-        assert np.array_equal(y3h, yo)  # ELLPACK blocks are sized to always fit the stream window
+        if loose:  # wide ELLPACK rows are walked warp-per-row as well
+            assert np.linalg.norm(y3h - yo) / np.linalg.norm(yo) < 1e-12
+        else:
+            assert np.array_equal(y3h, yo)
     else:
         assert L.b200_spmv_ellpack(dptr(rp), dptr(va), dptr(x), dptr(y), rows, 1001, 1.0, 0.0, None) == 1
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("shift", [0, 1, 3])
+def test_generic_csr_many_groups_per_warp(B, orc, torch_cuda, variant, shift):
+    """1200 x 1200 stencil through the GENERIC kernels: every persistent warp walks many 32-row groups
+    and several row_ptr chunks; `shift` mis-aligns all three arrays against the 16-byte bulk-copy
+    granularity (head / tail patches).  Bit-exact against the sequential-k oracle."""
+    torch = torch_cuda
+    L = B.load()
+    if L.b200_csr_variant_info(variant) is None:
+        pytest.skip("no such variant")
+    n = 1200
+    N = n * n
+    orp64, oci, ova = orc.stencil5_csr_direct(n)
+    orp = orp64.astype(np.int32)
+    rng = np.random.default_rng(7)
+    xh = rng.standard_normal(N)
+    yo = orc.csr_spmv(orp, oci, ova, xh)
+
+    def shifted(a):
+        t = torch.empty(len(a) + shift, dtype=torch.from_numpy(a[:1]).dtype, device="cuda")
+        t[shift:] = torch.from_numpy(a).cuda()
+        return t[shift:]
+    rp, ci, va = shifted(orp), shifted(oci), shifted(ova)
+    x = torch.from_numpy(xh).cuda()
+    y = torch.full((N,), float("nan"), dtype=torch.float64, device="cuda")
+    plan = B.CsrPlan()
+    B.check(L.b200_csr_plan_build(dptr(rp), N, len(ova), C.byref(plan), None), "plan")
+    plan.variant = variant
+    B.check(L.b200_spmv_csr(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x), dptr(y), N, 1.0, 0.0, None), "csr")
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), yo)
+    w, oidx, oval = orc.build_ellpack(orp, oci, ova, N, N)
+    assert w == 5
+    idx, val = shifted(oidx), shifted(oval)
+    y.fill_(float("nan"))
+    L.b200_csr_set_default_variant(variant)
+    try:
+        B.check(L.b200_spmv_ellpack(dptr(idx), dptr(val), dptr(x), dptr(y), N, w, 1.0, 0.0, None), "ell")
+        torch.cuda.synchronize()
+    finally:
+        L.b200_csr_set_default_variant(0)
+    assert np.array_equal(y.cpu().numpy(), yo)
 
 
 def test_stencil5_ellpack_kernel_signature(B, orc, torch_cuda):

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--what", default="stencil,cg,csr,ell")
     ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9,10,11")
     ap.add_argument("--rows", default="8,16,32,64,128")
+    ap.add_argument("--csr-variants", default="0")
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     a = ap.parse_args()
     what = a.what.split(",")
@@ -121,22 +122,30 @@ def main():
         rec("cg_reduce(1184 partials)", ms, best, 1184 * 8.0)
         del p, Ap, xx, r
 
+    cvars = [int(t) for t in a.csr_variants.split(",")]
     if "csr" in what:
         plan = B.CsrPlan()
         B.check(L.b200_csr_plan_build(dptr(rp), N, nnz, C.byref(plan), s), "plan")
-        ms, best = timeit(lambda: B.check(L.b200_spmv_csr(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x),
-                                                          dptr(y), N, 1.0, 0.0, s), "csr"))
-        ok = float(y.sum().item()) == N + 4 * n
-        rec("csr_adaptive", ms, best, 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N, rows_per_block=plan.rows_per_block, ok=ok)
+        for cv in cvars:
+            plan.variant = cv
+            y.fill_(float("nan"))
+            ms, best = timeit(lambda: B.check(L.b200_spmv_csr(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x),
+                                                              dptr(y), N, 1.0, 0.0, s), "csr"))
+            ok = float(y.sum().item()) == N + 4 * n
+            rec("csr_generic", ms, best, 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N, variant=cv, ok=ok)
 
     if "ell" in what:
         del ci, va, rp
         idx = torch.empty(5 * N + 2, dtype=torch.int32, device="cuda")
         val = torch.empty(5 * N + 2, dtype=torch.float64, device="cuda")
         B.check(L.b200_gen_stencil5_ellpack(n, 0, N, 5.0, -1.0, dptr(idx), dptr(val), s), "gen ell")
-        ms, best = timeit(lambda: B.check(L.b200_spmv_ellpack(dptr(idx), dptr(val), dptr(x), dptr(y), N, 5, 1.0, 0.0, s), "ell"))
-        ok = float(y.sum().item()) == N + 4 * n
-        rec("ellpack_generic", ms, best, 76.0 * N, ok=ok)
+        for cv in cvars:
+            L.b200_csr_set_default_variant(cv)
+            y.fill_(float("nan"))
+            ms, best = timeit(lambda: B.check(L.b200_spmv_ellpack(dptr(idx), dptr(val), dptr(x), dptr(y), N, 5, 1.0, 0.0, s), "ell"))
+            ok = float(y.sum().item()) == N + 4 * n
+            rec("ellpack_generic", ms, best, 76.0 * N, variant=cv, ok=ok)
+        L.b200_csr_set_default_variant(0)
         ms, best = timeit(lambda: B.check(L.b200_spmv_stencil5_ellpack(dptr(val), dptr(idx), dptr(x), dptr(y), N, 5, 1.0,
                                                                        0.0, n, s), "st-ell"))
         ok = float(y.sum().item()) == N + 4 * n
