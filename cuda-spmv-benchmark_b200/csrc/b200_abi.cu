@@ -239,14 +239,14 @@ struct CsrVariant {
 };
 // keep in sync with the dispatch switch in launch_csr
 const CsrVariant kCsrVariants[] = {
-    {8, 8, 128, "c0 (default): 8 warps/CTA, ring of 8 x 128-entry windows, 2 CTAs/SM"},
-    {4, 8, 128, "c1: 4 warps/CTA, ring of 8 x 128-entry windows, 4 CTAs/SM"},
+    {8, 4, 128, "c0 (default): 8 warps/CTA, ring of 4 x 128-entry windows, 4 CTAs/SM"},
+    {8, 4, 128, "c1: 8 warps/CTA, ring of 4 x 128-entry windows, 3 CTAs/SM"},
     {8, 4, 256, "c2: 8 warps/CTA, ring of 4 x 256-entry windows, 2 CTAs/SM"},
     {4, 4, 256, "c3: 4 warps/CTA, ring of 4 x 256-entry windows, 4 CTAs/SM"},
-    {8, 8, 64, "c4: 8 warps/CTA, ring of 8 x 64-entry windows, 3 CTAs/SM"},
-    {8, 4, 128, "c5: 8 warps/CTA, ring of 4 x 128-entry windows, 3 CTAs/SM"},
-    {8, 8, 64, "c6: 8 warps/CTA, ring of 8 x 64-entry windows, 4 CTAs/SM"},
-    {8, 4, 128, "c7: 8 warps/CTA, ring of 4 x 128-entry windows, 4 CTAs/SM"},
+    {8, 8, 64, "c4: 8 warps/CTA, ring of 8 x 64-entry windows, 4 CTAs/SM"},
+    {4, 4, 128, "c5: 4 warps/CTA, ring of 4 x 128-entry windows, 8 CTAs/SM"},
+    {8, 8, 128, "c6: 8 warps/CTA, ring of 8 x 128-entry windows, 2 CTAs/SM"},
+    {16, 4, 128, "c7: 16 warps/CTA, ring of 4 x 128-entry windows, 2 CTAs/SM"},
 };
 const int kNumCsrVariants = (int)(sizeof(kCsrVariants) / sizeof(kCsrVariants[0]));
 
@@ -254,9 +254,9 @@ std::atomic<int> g_csr_default_variant{0};
 int csr_default_variant() { return g_csr_default_variant.load(std::memory_order_relaxed); }
 constexpr int kCsrGroupsPerItem = 32;  // 1024 rows per warp item
 
-template <int WARPS, int STAGES, int WIN, bool ELL, int MINB>
-int launch_csr_ring(const CsrArgs& a, int gpw_override, cudaStream_t s) {
-    auto k = csr_ring_kernel<WARPS, STAGES, WIN, ELL, MINB>;
+template <int WARPS, int STAGES, int WIN, int MODE, int MINB>
+int launch_csr_ring_mode(const CsrArgs& a, int gpw_override, cudaStream_t s) {
+    auto k = csr_ring_kernel<WARPS, STAGES, WIN, MODE, MINB>;
     const size_t smem = (size_t)WARPS * csr_ring_warp_bytes<STAGES, WIN>();
     static int resident_ctas = 0;  // per instantiation: CTAs that fit the whole GPU at once
     if (resident_ctas == 0) {
@@ -291,17 +291,24 @@ int launch_csr_ring(const CsrArgs& a, int gpw_override, cudaStream_t s) {
     return check_launch("csr_ring_kernel");
 }
 
+template <int WARPS, int STAGES, int WIN, bool ELL, int MINB>
+int launch_csr_ring(const CsrArgs& a, int gpw, cudaStream_t s) {
+    if (!ELL) return launch_csr_ring_mode<WARPS, STAGES, WIN, 0, MINB>(a, gpw, s);
+    return csr_ring_ell_is_lpr<STAGES, WIN>(a.ell_width) ? launch_csr_ring_mode<WARPS, STAGES, WIN, 1, MINB>(a, gpw, s)
+                                                          : launch_csr_ring_mode<WARPS, STAGES, WIN, 2, MINB>(a, gpw, s);
+}
+
 template <bool ELL>
 int launch_csr_variant(int v, int gpw, const CsrArgs& a, cudaStream_t s) {
     switch (v) {
-        case 1: return launch_csr_ring<4, 8, 128, ELL, 4>(a, gpw, s);
+        case 1: return launch_csr_ring<8, 4, 128, ELL, 3>(a, gpw, s);
         case 2: return launch_csr_ring<8, 4, 256, ELL, 2>(a, gpw, s);
         case 3: return launch_csr_ring<4, 4, 256, ELL, 4>(a, gpw, s);
-        case 4: return launch_csr_ring<8, 8, 64, ELL, 3>(a, gpw, s);
-        case 5: return launch_csr_ring<8, 4, 128, ELL, 3>(a, gpw, s);
-        case 6: return launch_csr_ring<8, 8, 64, ELL, 4>(a, gpw, s);
-        case 7: return launch_csr_ring<8, 4, 128, ELL, 4>(a, gpw, s);
-        default: return launch_csr_ring<8, 8, 128, ELL, 2>(a, gpw, s);
+        case 4: return launch_csr_ring<8, 8, 64, ELL, 4>(a, gpw, s);
+        case 5: return launch_csr_ring<4, 4, 128, ELL, 8>(a, gpw, s);
+        case 6: return launch_csr_ring<8, 8, 128, ELL, 2>(a, gpw, s);
+        case 7: return launch_csr_ring<16, 4, 128, ELL, 2>(a, gpw, s);
+        default: return launch_csr_ring<8, 4, 128, ELL, 4>(a, gpw, s);
     }
 }
 
@@ -321,7 +328,7 @@ int launch_csr(const CsrArgs& a, int variant, cudaStream_t s) {
     const int gpw = variant / 1000;
     variant %= 1000;
     // the bulk copies need 16-byte aligned arrays; anything else takes the register-staged kernel
-    const bool aligned = (((uintptr_t)a.col_idx | (uintptr_t)a.values | (uintptr_t)a.row_ptr) & 15) == 0;
+    const bool aligned = (((uintptr_t)a.col_idx | (uintptr_t)a.values) & 15) == 0;
     if (variant == 100 || !aligned) return launch_csr_legacy(a, s);
     if (variant >= kNumCsrVariants) variant = 0;
     return a.row_ptr ? launch_csr_variant<false>(variant, gpw, a, s) : launch_csr_variant<true>(variant, gpw, a, s);

@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 //   * Lane 0 streams the range in fixed windows of WIN entries into a warp-private circular
 //     shared-memory buffer of STAGES windows with 1-D bulk async copies (TMA engine, SASS UBLKCP;
 //     mbarrier complete_tx, L2 evict-first): independent of where rows begin, no registers tied
-//     up, up to STAGES-1 windows in flight per warp.  row_ptr travels the same way through a small
-//     second ring (chunks of 128 rows).
+//     up, up to STAGES-1 windows in flight per warp.  Row extents are plain coalesced loads issued
+//     one pipeline turn before they are needed.
 //   * Short rows ("lane per row", groups with at most RING/2 - WIN entries and rows no longer than
 //     `vector_threshold`): every lane owns one row of the group.  One group AHEAD of the
 //     arithmetic it reads its first 8 column ids from shared memory and launches the x gathers
@@ -157,38 +157,40 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 //     (k - row_start) % 32 == l in k order, butterfly sum at the row end (rounding-level
 //     difference to the sequential order, documented tolerance 1e-12).  Rows may be longer than
 //     the ring: they stream through it window by window.
-// Only __syncwarp is used; warps are fully independent.  All three arrays must be 16-byte aligned
+// Only __syncwarp is used; warps are fully independent.  col_idx and values must be 16-byte aligned
 // (the launcher routes anything else to csr_warp_stream_kernel above).
 // ================================================================================================
-constexpr int kCsrRpChunk = 128;  // rows per row_ptr ring slot (4 groups)
-constexpr int kCsrRpSlot = kCsrRpChunk + 8;
 constexpr int kCsrPrefetch = 8;  // x values per row gathered one group ahead
 constexpr int kCsrMirror = 32;   // ring[0, 32) is mirrored behind the ring end: a lane-per-row row
                                  // (at most 32 entries) never wraps, its shared addresses are base + j
 
 // lane-per-row step 1: column ids of the lane's first N entries -> x gathers in flight.  The loads are
-// unconditional (slots past the row end read x[0]) so that they compile to straight-line code.
-template <int N, bool ELL>
+// unconditional (slots past the row end read x[0]) so that they compile to straight-line code;
+// FULL = every row of the group has exactly N entries (no per-lane predicates at all).
+// ELLPACK padding (column -1, value 0.0 as written by the builders): x is replaced by 0, and
+// fma(0.0, 0.0, sum) leaves the sum untouched.
+template <int N, bool ELL, bool FULL>
 __device__ __forceinline__ void lpr_gather(const int* __restrict__ pc, int len, const double* __restrict__ x,
-                                           double (&xq)[kCsrPrefetch], uint32_t& pm) {
+                                           double (&xq)[kCsrPrefetch]) {
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        int c = (j < len) ? pc[j] : 0;
+        int c = pc[j];  // always inside the ring (+ mirror); meaningful only for j < len
+        if (!FULL) c = (j < len) ? c : 0;
         if (ELL) {
-            pm |= (c >= 0 ? 1u : 0u) << j;
-            c = max(c, 0);
+            const double xv = __ldg(x + (unsigned)max(c, 0));
+            xq[j] = c >= 0 ? xv : 0.0;
+        } else {
+            xq[j] = __ldg(x + (unsigned)c);
         }
-        xq[j] = __ldg(x + c);
     }
 }
 // lane-per-row step 2: the k-ordered fma chain over the first N entries
-template <int N, bool ELL>
-__device__ __forceinline__ double lpr_chain(const double* __restrict__ pv, int len, const double (&xq)[kCsrPrefetch],
-                                            uint32_t pm) {
+template <int N, bool FULL>
+__device__ __forceinline__ double lpr_chain(const double* __restrict__ pv, int len, const double (&xq)[kCsrPrefetch]) {
     double sum = 0.0;
 #pragma unroll
     for (int j = 0; j < N; j++)
-        if (j < len && (!ELL || ((pm >> j) & 1u))) sum = fma(pv[j], xq[j], sum);
+        if (FULL || j < len) sum = fma(pv[j], xq[j], sum);
     return sum;
 }
 #define B200_CSR_DISPATCH_N(n, CALL)                                                              \
@@ -205,10 +207,14 @@ __device__ __forceinline__ double lpr_chain(const double* __restrict__ pv, int l
     }
 
 template <int STAGES, int WIN>
+constexpr bool csr_ring_ell_is_lpr(int width) {
+    return 32 * width <= STAGES * WIN - 2 * WIN && width <= kCsrMirror;
+}
+
+template <int STAGES, int WIN>
 __host__ __device__ constexpr size_t csr_ring_warp_bytes() {
     return (size_t)(STAGES * WIN + kCsrMirror) * 12  // values + column ring (+ wrap mirror)
-           + (size_t)2 * kCsrRpSlot * 4         // row_ptr ring
-           + (size_t)(STAGES + 2) * 8;          // mbarriers
+           + (size_t)STAGES * 8;                     // mbarriers
 }
 
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
@@ -237,17 +243,22 @@ struct CsrGroup {
     int s, len;            // per lane: local start of its row, row length
     int gs, nnz, maxlen;   // uniform: local start of the group, its entries, longest row
     bool lpr;              // uniform: lane-per-row (else warp-per-row)
+    bool full;             // uniform: all 32 rows have exactly maxlen entries
 };
 
-template <int WARPS, int STAGES, int WIN, bool ELL, int MINB>
+// MODE: 0 = CSR (every group picks lane-per-row or warp-per-row), 1 = ELLPACK narrow enough for
+// lane-per-row throughout, 2 = wide ELLPACK, warp-per-row throughout (the host picks with
+// csr_ring_ell_is_lpr).
+template <int WARPS, int STAGES, int WIN, int MODE, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArgs a, const int groups_per_warp) {
+    constexpr bool ELL = MODE != 0;
     constexpr int RING = STAGES * WIN, M = RING - 1, J = kCsrPrefetch;
     constexpr int LIMIT = RING - 2 * WIN;  // a lane-per-row group must fit the ring beside one window in flight
-    constexpr int RC = kCsrRpChunk, RSLOT = kCsrRpSlot;
     static_assert((RING & M) == 0 && (STAGES & (STAGES - 1)) == 0, "ring sizes must be powers of two");
     static_assert(LIMIT >= 32, "ring too small");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(B200_FULL, threadIdx.x >> 5, 0);  // tells the compiler it is warp-uniform
 
     const long long Ra = ((long long)blockIdx.x * WARPS + warp) * groups_per_warp * 32;
     if (Ra >= a.n_rows) return;
@@ -257,42 +268,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     unsigned char* wbase = smem_raw + (size_t)warp * csr_ring_warp_bytes<STAGES, WIN>();
     double* sval = reinterpret_cast<double*>(wbase);
     int* scol = reinterpret_cast<int*>(sval + RING + kCsrMirror);
-    int* srp = scol + RING + kCsrMirror;
-    const uint32_t sval_a = smem_u32(sval), scol_a = smem_u32(scol), srp_a = smem_u32(srp);
-    const uint32_t bar_a = smem_u32(srp + 2 * RSLOT);  // [0,STAGES) windows, then 2 row_ptr slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scol + RING + kCsrMirror);
+    const uint32_t sval_a = smem_u32(sval), scol_a = smem_u32(scol), bar_a = smem_u32(bars);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < STAGES + 2; i++) mbar_init(reinterpret_cast<uint64_t*>(srp + 2 * RSLOT) + i, 1);
+        for (int i = 0; i < STAGES; i++) mbar_init(bars + i, 1);
         mbar_fence_init();
     }
     __syncwarp();
     const uint64_t policy = l2_policy_evict_first();
     const double* __restrict__ xp = a.x;
-
-    // ---------------------------------------------------------------- row_ptr ring (CSR only)
-    const int n_chunks = (nrows + RC - 1) / RC;
-    const long long rp_t4 = ((a.n_rows + 1) & ~3LL) - Ra;  // bulk-copyable row_ptr entries, item-local
-    auto issue_rp = [&](int c) {
-        const long long left = rp_t4 - (long long)c * RC;
-        const int cnt = left < RC + 4 ? (int)left : RC + 4;
-        if (lane == 0 && cnt > 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bar = bar_a + (STAGES + (c & 1)) * 8;
-            mbar_expect_tx_a(bar, cnt * 4);
-            bulk_g2s_a(srp_a + (c & 1) * RSLOT * 4, a.row_ptr + Ra + (long long)c * RC, cnt * 4, bar, policy);
-        }
-    };
-    auto wait_rp = [&](int c) {
-        const long long left = rp_t4 - (long long)c * RC;
-        if (left > 0) mbar_wait_a(bar_a + (STAGES + (c & 1)) * 8, (c >> 1) & 1);
-        if (left < RC + 1) {  // tail of row_ptr the 16-byte granularity could not cover (last chunk only)
-            const int lo = left > 0 ? (int)left : 0;
-            const int hi = min(RC, nrows - c * RC) + 1;
-            int* dst = srp + (c & 1) * RSLOT;
-            for (int k = lo + lane; k < hi; k += 32) dst[k] = a.row_ptr[Ra + (long long)c * RC + k];
-        }
-        __syncwarp();
-    };
 
     long long K0, K1, total;
     if (ELL) {
@@ -300,7 +285,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
         K1 = (Ra + nrows) * a.ell_width;
         total = a.n_rows * a.ell_width;
     } else {
-        issue_rp(0);
         long long t = 0;
         if (lane == 0) t = a.row_ptr[Ra];
         if (lane == 1) t = a.row_ptr[Ra + nrows];
@@ -325,8 +309,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     auto issue_window = [&](int j) {
         const int cnt = min(WIN, tl4 - j * WIN);
         if (lane == 0 && cnt > 0) {
-            // order the slot's earlier generic-proxy reads before the async-proxy writes
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // WAR on the slot: every lane's shared loads from it were consumed before the __syncwarp
+            // in release(); reads need no proxy fence against the async-proxy write that follows
             const int slot = j & (STAGES - 1);
             const uint32_t bar = bar_a + slot * 8;
             mbar_expect_tx_a(bar, cnt * 12);
@@ -338,7 +322,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     auto ensure = [&](int kend) {
         while (landed_end < kend) {
             const int j = landed;
-            if (tl4 > j * WIN) mbar_wait_a(bar_a + (j & (STAGES - 1)) * 8, (j / STAGES) & 1);
+            if (tl4 > j * WIN) mbar_wait_a(bar_a + (j & (STAGES - 1)) * 8, ((unsigned)j / STAGES) & 1u);
             if ((j + 1) * WIN > tl4) {  // array tail outside the 16-byte granules (matrix end only)
                 const int lo = max(tl4, j * WIN), hi = min(totl, (j + 1) * WIN);
                 for (int k = lo + lane; k < hi; k += 32) {
@@ -369,42 +353,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
         if (issued < nwin) issue_window(issued++);
 
     // ---------------------------------------------------------------- groups
-    int cur_chunk = -1;
-    auto load_group = [&](int gi, CsrGroup& G) {
-        const int r0 = min(gi * 32 + lane, nrows), r1 = min(gi * 32 + lane + 1, nrows);
-        int e;
-        if (ELL) {
-            G.s = k0l + r0 * a.ell_width;
-            e = k0l + r1 * a.ell_width;
-        } else {
-            const int c = min(gi / (RC / 32), n_chunks - 1);  // gi >= ngroups: empty sentinel group
-            if (c != cur_chunk) {
-                __syncwarp();
-                if (c + 1 < n_chunks) issue_rp(c + 1);  // into the slot of chunk c-1: every lane is done with it
-                wait_rp(c);
-                cur_chunk = c;
-            }
-            const int* rp = srp + (c & 1) * RSLOT - c * RC;
-            G.s = rp[r0] - wk0i;
-            e = rp[r1] - wk0i;
+    // Row extents: lane l of group gi needs row_ptr[gi*32 + l + 1] (its row end); the row start is the
+    // neighbour lane's end.  The load is issued one pipeline turn before the values are looked at.
+    const int* __restrict__ rowp = ELL ? nullptr : a.row_ptr + Ra;
+    int e_raw = 0, e_raw1 = 0, e_raw2 = 0;  // row_ptr entries in flight for the three groups after `nxt`
+    int carry = k0l;        // local end of the previous group = start of the next one
+    auto fetch_extents = [&](int gi) {  // queue: e_raw is consumed next, the new load goes to the back
+        if (!ELL) {
+            e_raw = e_raw1;
+            e_raw1 = e_raw2;
+            e_raw2 = __ldg(rowp + min(gi * 32 + lane + 1, nrows));
         }
+    };
+    auto make_group = [&](int gi, CsrGroup& G) {  // gi >= ngroups: empty sentinel group
+        int e;
+        if (ELL) e = k0l + min(gi * 32 + lane + 1, nrows) * a.ell_width;
+        else e = e_raw - wk0i;
+        const int up = __shfl_up_sync(B200_FULL, e, 1);
+        G.s = lane == 0 ? carry : up;
         G.len = e - G.s;
-        G.gs = __shfl_sync(B200_FULL, G.s, 0);
-        G.nnz = __shfl_sync(B200_FULL, e, 31) - G.gs;
-        G.maxlen = __reduce_max_sync(B200_FULL, G.len);
-        G.lpr = G.nnz <= LIMIT && G.maxlen <= min(a.vector_threshold, kCsrMirror);
+        G.gs = carry;
+        carry = __shfl_sync(B200_FULL, e, 31);
+        G.nnz = carry - G.gs;
+        if (ELL) {  // uniform rows: nothing to decide per group
+            G.maxlen = a.ell_width;
+            G.lpr = MODE == 1;
+            G.full = (gi + 1) * 32 <= nrows;
+        } else {
+            G.maxlen = __reduce_max_sync(B200_FULL, G.len);
+            G.lpr = G.nnz <= LIMIT && G.maxlen <= min(a.vector_threshold, kCsrMirror);
+            G.full = G.nnz == 32 * G.maxlen;
+        }
     };
     // lane-per-row, step 1 (one group ahead): column ids -> x gathers in flight
-    auto prefetch = [&](const CsrGroup& G, double (&xq)[J], uint32_t& pm) {
-        pm = 0;
+    auto prefetch = [&](const CsrGroup& G, double (&xq)[J]) {
         const int* pc = scol + (G.s & M);
-        B200_CSR_DISPATCH_N(G.maxlen, (lpr_gather<N_, ELL>(pc, G.len, xp, xq, pm)));
+        if (G.full) {
+            B200_CSR_DISPATCH_N(G.maxlen, (lpr_gather<N_, ELL, true>(pc, G.len, xp, xq)));
+        } else {
+            B200_CSR_DISPATCH_N(G.maxlen, (lpr_gather<N_, ELL, false>(pc, G.len, xp, xq)));
+        }
     };
     // lane-per-row, step 2: the k-ordered fma chain of this lane's row
-    auto process_lpr = [&](const CsrGroup& G, const double (&xq)[J], uint32_t pm) {
+    auto process_lpr = [&](const CsrGroup& G, const double (&xq)[J]) {
         double sum = 0.0;
         const double* pv = sval + (G.s & M);
-        B200_CSR_DISPATCH_N(G.maxlen, (sum = lpr_chain<N_, ELL>(pv, G.len, xq, pm)));
+        if (G.full) {
+            B200_CSR_DISPATCH_N(G.maxlen, (sum = lpr_chain<N_, true>(pv, G.len, xq)));
+        } else {
+            B200_CSR_DISPATCH_N(G.maxlen, (sum = lpr_chain<N_, false>(pv, G.len, xq)));
+        }
         if (G.maxlen > J) {  // rows longer than the prefetch depth
             const int* pc = scol + (G.s & M);
             for (int j = J; j < G.maxlen; j++) {
@@ -446,15 +444,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     // The x gathers of `nxt` are in flight while everything behind them runs; behind the last group
     // come empty sentinel groups, so there is no "has next" case.
     double xq[J];
-    uint32_t pm = 0;
     CsrGroup cur, nxt;
     double* yp = a.y + Ra + lane;
     const double alpha = a.alpha, beta = a.beta;
-    cur.lpr = true; cur.s = cur.len = cur.gs = cur.nnz = cur.maxlen = 0;
+    cur.lpr = true; cur.full = false; cur.s = cur.len = cur.gs = cur.nnz = cur.maxlen = 0;
     nxt = cur;
+    fetch_extents(0);
+    fetch_extents(1);
+    fetch_extents(2);
     for (int gi = -2; gi < ngroups; gi++) {  // two warm-up turns fill the pipeline through the same code
         if (gi >= 0) {
-            const double sum = cur.lpr ? process_lpr(cur, xq, pm) : process_vec(cur, min(32, nrows - gi * 32));
+            double sum;
+            if (MODE == 1) sum = process_lpr(cur, xq);
+            else if (MODE == 2) sum = process_vec(cur, min(32, nrows - gi * 32));
+            else sum = cur.lpr ? process_lpr(cur, xq) : process_vec(cur, min(32, nrows - gi * 32));
             if (gi * 32 + lane < nrows) {
                 if (beta == 0.0) *yp = alpha * sum;
                 else *yp = fma(alpha, sum, beta * *yp);
@@ -463,13 +466,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
         }
         if (gi >= -1) {
             release(nxt.gs);
-            if (nxt.lpr) {
+            if (MODE == 1 || (MODE == 0 && nxt.lpr)) {
                 ensure(nxt.gs + nxt.nnz);
-                prefetch(nxt, xq, pm);
+                prefetch(nxt, xq);
             }
         }
         cur = nxt;
-        load_group(gi + 2, nxt);
+        make_group(gi + 2, nxt);
+        fetch_extents(gi + 5);
     }
 }
 
