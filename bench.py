@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--grid", type=int, default=20000)
     ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-operators", action="store_true", help="skip the 10k x 10k operator comparison (configs[1])")
     return ap.parse_args()
 
 
@@ -144,6 +145,63 @@ def run_reference(args):
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[1]: 10k x 10k single-GPU SpMV, STENCIL5 vs generic CSR vs generic ELLPACK (extra keys)
+# ------------------------------------------------------------------------------------------------
+def operator_table(L, B, torch, peak, n=10000, reps=10, warm=5):
+    """Kernel-only times (CUDA events on the launching stream, median of `reps` after `warm`
+    warm-ups, the reference's own protocol -- src/main/main.cu:136-137, benchmark_stats.cu:39-89)
+    through the C ABI, x = 1.  GB/s from the ALGORITHMIC bytes of SURVEY.md section 8(d)."""
+    N, nnz = n * n, 5 * n * n - 4 * n
+    s = torch.cuda.current_stream().cuda_stream
+    dp = lambda t: C.c_void_p(t.data_ptr())
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def row(ms, nbytes, y):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": round(ms, 4), "gb_s": round(gbs, 1), "frac_of_peak": round(gbs / peak, 3),
+                "bytes": nbytes, "checksum_ok": float(y.sum().item()) == N + 4 * n}
+
+    out = {"grid": n, "rows": N, "nnz": nnz, "x": "ones", "protocol": "%d warm-up + median of %d" % (warm, reps)}
+    rp = torch.empty(N + 1, dtype=torch.int32, device="cuda")
+    ci = torch.empty(nnz + 2, dtype=torch.int32, device="cuda")
+    va = torch.zeros(nnz + 2, dtype=torch.float64, device="cuda")
+    B.check(L.b200_gen_stencil5_csr(n, 0, N, 5.0, -1.0, dp(rp), dp(ci), dp(va), s), "gen csr")
+    x = torch.ones(N, dtype=torch.float64, device="cuda")
+    y = torch.empty(N, dtype=torch.float64, device="cuda")
+    ms = timed(lambda: B.check(L.b200_spmv_stencil5_csr(dp(rp), dp(ci), dp(va), dp(x), dp(y), N, n, s), "stencil5"))
+    out["stencil5-csr"] = row(ms, 8.0 * nnz + 16.0 * N, y)
+    plan = B.CsrPlan()
+    B.check(L.b200_csr_plan_build(dp(rp), N, nnz, C.byref(plan), s), "plan")
+    y.fill_(float("nan"))
+    ms = timed(lambda: B.check(L.b200_spmv_csr(C.byref(plan), dp(rp), dp(ci), dp(va), dp(x), dp(y), N, 1.0, 0.0, s), "csr"))
+    out["csr"] = row(ms, 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N, y)
+    del rp, ci, va
+    idx = torch.empty(5 * N + 2, dtype=torch.int32, device="cuda")
+    val = torch.empty(5 * N + 2, dtype=torch.float64, device="cuda")
+    B.check(L.b200_gen_stencil5_ellpack(n, 0, N, 5.0, -1.0, dp(idx), dp(val), s), "gen ell")
+    y.fill_(float("nan"))
+    ms = timed(lambda: B.check(L.b200_spmv_ellpack(dp(idx), dp(val), dp(x), dp(y), N, 5, 1.0, 0.0, s), "ellpack"))
+    out["ellpack"] = row(ms, 76.0 * N, y)
+    y.fill_(float("nan"))
+    ms = timed(lambda: B.check(L.b200_spmv_stencil5_ellpack(dp(val), dp(idx), dp(x), dp(y), N, 5, 1.0, 0.0, n, s), "st-ell"))
+    out["stencil5-ellpack"] = row(ms, 56.0 * N, y)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -290,6 +348,10 @@ def run_b200(args):
                                         "halo_push", "residual_init", "reduce_rr0"], [round(v, 4) for v in phase_sum])),
         "clocks": clocks,
     }
+    if world == 1 and not args.no_operators:
+        op.contents.free()
+        torch.cuda.empty_cache()
+        line["operators_10k"] = operator_table(L, B, torch, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, sample = cpu_cg_sample(n, args.cpu_grid)
         line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": threads, "kind": "port", "sample": sample}

@@ -5,20 +5,17 @@
 // (include/spmv_ellpack.h:28-51).  Semantics = the reference's scalar CSR kernel
 // (src/solvers/cg_solver_mgpu_partitioned.cu:40-56): sum_k fma(v[k], x[col[k]], sum), k ascending.
 //
-// Scheme ("warp-stream", chosen per 32-row group from the row lengths; the per-matrix row-length
-// histogram taken at plan time sets the long-row threshold):
-//   * A WARP owns 32 consecutive rows.  Their non-zeros are one contiguous range of col_idx /
-//     values, which the warp sweeps in windows of 256 entries with perfectly coalesced loads
-//     (lane k, k+32, ... -- independent of where rows begin), gathers x[col] for all of them at
-//     once (8 independent loads per lane in flight) and parks value and x side by side in its
-//     private shared-memory slice.  Then each lane adds the products of ITS row that fall into the
-//     window, in k order, carrying the running sum across windows.  The result is bit-identical to
-//     the scalar reference order, there is no block-wide barrier (only __syncwarp), and HBM only
-//     sees full-line bursts -- the scalar kernel issues strided 12-byte requests per lane.
-//   * Groups whose rows are long (more than `vector_threshold` entries per row on average) are
-//     processed warp-per-row instead: lanes stride over the row, fixed-order butterfly sum (order
-//     differs from the scalar reference => equal to rounding only, documented tolerance 1e-12).
-// ELLPACK (row-major, padding index -1) is the same kernel with row_ptr[r] = r * width.
+// Two kernels live here:
+//   * csr_ring_kernel (below, the production path): warp-private bulk-copy ring, lane-per-row with
+//     x gathered one group ahead for short rows, warp-per-row streaming for long rows; the scheme
+//     is picked per 32-row group, the long-row threshold comes from the plan's row-length histogram.
+//   * csr_warp_stream_kernel ("warp-stream", register staged): the first-generation kernel, used
+//     when col_idx / values are not 16-byte aligned and kept as variant 100 for A/B measurements.
+//     A WARP owns 32 consecutive rows, sweeps their contiguous non-zero range in windows of 256
+//     entries with coalesced loads, gathers x[col] for all of them at once, parks value and x side
+//     by side in shared memory, then each lane adds the products of ITS row in k order (bit-exact);
+//     groups with long rows go warp-per-row (butterfly sum, tolerance 1e-12).
+// ELLPACK (row-major, padding index -1) is the same code with row_ptr[r] = r * width.
 #pragma once
 #include "common.cuh"
 
@@ -32,7 +29,8 @@ struct CsrArgs {
     double* y;
     long long n_rows;
     int ell_width;
-    int vector_threshold;  // mean entries per row of a 32-row group above which it goes warp-per-row
+    int vector_threshold;  // ring kernel: longest row of a 32-row group above which it goes warp-per-row
+                           // (warp-stream kernel: mean entries per row of the group)
     double alpha, beta;
 };
 
@@ -146,8 +144,8 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 //   * Lane 0 streams the range in fixed windows of WIN entries into a warp-private circular
 //     shared-memory buffer of STAGES windows with 1-D bulk async copies (TMA engine, SASS UBLKCP;
 //     mbarrier complete_tx, L2 evict-first): independent of where rows begin, no registers tied
-//     up, up to STAGES-1 windows in flight per warp.  Row extents are plain coalesced loads issued
-//     one pipeline turn before they are needed.
+//     up, up to STAGES-1 windows in flight per warp.  Row extents are coalesced 4-byte cp.async
+//     loads into a small shared-memory queue, issued three pipeline turns before they are needed.
 //   * Short rows ("lane per row", groups with at most RING/2 - WIN entries and rows no longer than
 //     `vector_threshold`): every lane owns one row of the group.  One group AHEAD of the
 //     arithmetic it reads its first 8 column ids from shared memory and launches the x gathers
@@ -161,6 +159,7 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 // (the launcher routes anything else to csr_warp_stream_kernel above).
 // ================================================================================================
 constexpr int kCsrPrefetch = 8;  // x values per row gathered one group ahead
+constexpr int kCsrExtentSlots = 4;  // row extents of 3 groups in flight (cp.async) + 1 being read
 constexpr int kCsrMirror = 32;   // ring[0, 32) is mirrored behind the ring end: a lane-per-row row
                                  // (at most 32 entries) never wraps, its shared addresses are base + j
 
@@ -214,6 +213,7 @@ constexpr bool csr_ring_ell_is_lpr(int width) {
 template <int STAGES, int WIN>
 __host__ __device__ constexpr size_t csr_ring_warp_bytes() {
     return (size_t)(STAGES * WIN + kCsrMirror) * 12  // values + column ring (+ wrap mirror)
+           + (size_t)kCsrExtentSlots * 32 * 4        // row extents queue (cp.async landing slots)
            + (size_t)STAGES * 8;                     // mbarriers
 }
 
@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     unsigned char* wbase = smem_raw + (size_t)warp * csr_ring_warp_bytes<STAGES, WIN>();
     double* sval = reinterpret_cast<double*>(wbase);
     int* scol = reinterpret_cast<int*>(sval + RING + kCsrMirror);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scol + RING + kCsrMirror);
+    int* sext = scol + RING + kCsrMirror;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sext + kCsrExtentSlots * 32);
     const uint32_t sval_a = smem_u32(sval), scol_a = smem_u32(scol), bar_a = smem_u32(bars);
     if (lane == 0) {
 #pragma unroll
@@ -296,10 +297,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     // item-local entry index = absolute index - wk0 (wk0 16-byte aligned for both arrays)
     const long long wk0 = K0 & ~3LL;
     const int k0l = (int)(K0 - wk0), k1l = (int)(K1 - wk0);
-    const long long t4 = (total & ~3LL) - wk0, tt = total - wk0;
+    const long long t4 = (total & ~3LL) - wk0;
     const int tl4 = t4 > 0x7fffff00LL ? 0x7fffff00 : (int)t4;   // bulk-copyable entries
-    const int totl = tt > 0x7fffff00LL ? 0x7fffff00 : (int)tt;  // readable entries
     const int nwin = (k1l > k0l) ? (k1l + WIN - 1) / WIN : 0;
+    const int lim4 = min(tl4, (k1l + 3) & ~3);  // bulk copies stop at the item's end (16-byte granule)
     const int* colp = a.col_idx + wk0;
     const double* valp = a.values + wk0;
     const int wk0i = (int)wk0;  // CSR: absolute entry indices are ints
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     // ---------------------------------------------------------------- window ring
     int issued = 0, landed = 0, landed_end = 0, released_end = WIN;  // landed_end = landed * WIN
     auto issue_window = [&](int j) {
-        const int cnt = min(WIN, tl4 - j * WIN);
+        const int cnt = min(WIN, lim4 - j * WIN);
         if (lane == 0 && cnt > 0) {
             // WAR on the slot: every lane's shared loads from it were consumed before the __syncwarp
             // in release(); reads need no proxy fence against the async-proxy write that follows
@@ -322,9 +323,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     auto ensure = [&](int kend) {
         while (landed_end < kend) {
             const int j = landed;
-            if (tl4 > j * WIN) mbar_wait_a(bar_a + (j & (STAGES - 1)) * 8, ((unsigned)j / STAGES) & 1u);
-            if ((j + 1) * WIN > tl4) {  // array tail outside the 16-byte granules (matrix end only)
-                const int lo = max(tl4, j * WIN), hi = min(totl, (j + 1) * WIN);
+            if (lim4 > j * WIN) mbar_wait_a(bar_a + (j & (STAGES - 1)) * 8, ((unsigned)j / STAGES) & 1u);
+            if ((j + 1) * WIN > lim4 && k1l > lim4) {  // array tail outside the 16-byte granules (matrix end only)
+                const int lo = max(lim4, j * WIN), hi = min(k1l, (j + 1) * WIN);
                 for (int k = lo + lane; k < hi; k += 32) {
                     sval[k & M] = valp[k];
                     scol[k & M] = colp[k];
@@ -356,19 +357,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     // Row extents: lane l of group gi needs row_ptr[gi*32 + l + 1] (its row end); the row start is the
     // neighbour lane's end.  The load is issued one pipeline turn before the values are looked at.
     const int* __restrict__ rowp = ELL ? nullptr : a.row_ptr + Ra;
-    int e_raw = 0, e_raw1 = 0, e_raw2 = 0;  // row_ptr entries in flight for the three groups after `nxt`
-    int carry = k0l;        // local end of the previous group = start of the next one
-    auto fetch_extents = [&](int gi) {  // queue: e_raw is consumed next, the new load goes to the back
+    // The loads are 4-byte cp.async straight into a small shared-memory queue (one slot of 32 ints per
+    // group, 3 groups in flight): no register waits on them until the group is actually built.
+    int carry = k0l;  // local end of the previous group = start of the next one
+    const uint32_t sext_a = smem_u32(sext) + lane * 4;
+    auto fetch_extents = [&](int gi) {
         if (!ELL) {
-            e_raw = e_raw1;
-            e_raw1 = e_raw2;
-            e_raw2 = __ldg(rowp + min(gi * 32 + lane + 1, nrows));
+            // (a 4-byte cp.async does not take an L2 cache hint: illegal instruction on sm_100a)
+            const int* src = rowp + min(gi * 32 + lane + 1, nrows);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sext_a + (gi & (kCsrExtentSlots - 1)) * 128),
+                         "l"(src)
+                         : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
     };
     auto make_group = [&](int gi, CsrGroup& G) {  // gi >= ngroups: empty sentinel group
         int e;
         if (ELL) e = k0l + min(gi * 32 + lane + 1, nrows) * a.ell_width;
-        else e = e_raw - wk0i;
+        else {
+            asm volatile("cp.async.wait_group 2;" ::: "memory");  // all but the two youngest fetches landed
+            e = sext[(gi & (kCsrExtentSlots - 1)) * 32 + lane] - wk0i;
+        }
         const int up = __shfl_up_sync(B200_FULL, e, 1);
         G.s = lane == 0 ? carry : up;
         G.len = e - G.s;
@@ -459,8 +468,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
             else if (MODE == 2) sum = process_vec(cur, min(32, nrows - gi * 32));
             else sum = cur.lpr ? process_lpr(cur, xq) : process_vec(cur, min(32, nrows - gi * 32));
             if (gi * 32 + lane < nrows) {
-                if (beta == 0.0) *yp = alpha * sum;
-                else *yp = fma(alpha, sum, beta * *yp);
+                if (beta == 0.0) __stcs(yp, alpha * sum);
+                else __stcs(yp, fma(alpha, sum, beta * *yp));
             }
             yp += 32;
         }

@@ -92,9 +92,9 @@ const char* b200_stencil5_variant_info(int v);
 
 /* ---- generic CSR / ELLPACK (no cuSPARSE) ------------------------------------------------ */
 typedef struct {
-    int rows_per_block;       /* rows per CTA (32 per warp) */
-    int window;               /* shared-memory window per warp, in non-zeros */
-    int vector_threshold;     /* mean row length of a 32-row group above which it runs warp-per-row */
+    int rows_per_block;       /* rows per warp item */
+    int window;               /* bulk-copy window, in non-zeros */
+    int vector_threshold;     /* longest row of a 32-row group above which it runs warp-per-row */
     int variant;              /* tuning variant (0 = default), see b200_csr_variant_info */
     unsigned long long hist[33]; /* rows with length in (2^(b-1), 2^b] */
     unsigned long long max_row_len;
