@@ -311,18 +311,40 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     rows_local = nl
     nnz_local = L.b200_stencil5_nnz_before(off + nl, n) - L.b200_stencil5_nnz_before(off, n)
-    k1_bytes = 8.0 * nnz_local + 16.0 * rows_local  # values + p once + Ap   
+    # Dominant kernel: the STENCIL5 SpMV.  Deferred-x schedule (default): the first launch of a solve is
+    # the plain SpMV + p.Ap (values + p + Ap = 8 nnz + 16 N bytes), every later one is the fused
+    # direction-update SpMV (values + r + p_old + x in, p_new + x + Ap out = 8 nnz + 48 N bytes);
+    # B200_CG_SCHEDULE=classic runs the plain one every iteration.
+    deferred_x = os.environ.get("B200_CG_SCHEDULE", "") != "classic"
+    dot_bytes = 8.0 * nnz_local + 16.0 * rows_local
+    fused_bytes = 8.0 * nnz_local + 48.0 * rows_local
+    if deferred_x and iters and iters > 1:
+        k1_bytes = (dot_bytes + (iters - 1) * fused_bytes) / iters  # mean over the launches of a solve
+        k1_name = "stencil5_kernel<ST_FUSED> (p = r + beta p, x += alpha p, SpMV, p.Ap; 1 of %d launches is the plain ST_DOT)" % iters
+        traffic_key = "stencil5_fused_dram_bytes_per_launch_%d" % n
+        traffic_alg = fused_bytes
+    else:
+        k1_bytes = dot_bytes
+        k1_name = "stencil5_kernel<ST_DOT> (SpMV + p.Ap)"
+        traffic_key = "stencil5_dot_dram_bytes_per_launch_%d" % n
+        traffic_alg = dot_bytes
     k1_avg_ms = k1_ms / max(k1_cnt, 1)
     achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_cnt else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("stencil5_dot_dram_bytes_per_launch_%d" % n)
+            traffic = json.load(open(tp)).get(traffic_key)
             if traffic is not None:  # captured on the full matrix: scale to this rank's band
                 traffic = traffic * nnz_local / float(5 * N - 4 * n)
         except Exception:
             traffic = None
+    if deferred_x:
+        iter_bytes = 112.0 * rows_local          # K1F 88 + K2r 24 (interior rows)
+        solve_bytes = (72.0 + 56.0 + 88.0 * (iters - 1) + 24.0 * iters + 24.0) * rows_local
+    else:
+        iter_bytes = 128.0 * rows_local          # K1 56 + K2 48 + K3 24
+        solve_bytes = (72.0 + 128.0 * iters) * rows_local
     line = {
         "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -335,17 +357,22 @@ def run_b200(args):
                 "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
                 "host_buffers": "pinned", "block_wall_ms_per_step": block_ms / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "stencil5_kernel<ST_DOT> (SpMV + p.Ap)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt},
-        "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV+dot launch inside CG"},
+                     "bytes_per_launch": k1_bytes, "traffic_kernel_algorithmic_bytes": traffic_alg,
+                     "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt},
+        "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV launch inside CG (see roofline.kernel)"},
         "cg": {"iterations": iters, "residual_norm": stats.residual_norm, "solution_sum": stats.solution_sum,
                "solution_norm": stats.solution_norm,
-               "iter_bytes_model": 128.0 * rows_local,
-               "solve_gb_s": (14 * 128.0 + 104.0) * rows_local / (ms * 1e-3) / 1e9},
-        "phases_ms_per_step": dict(zip(["_", "spmv_dot(K1)", "reduce_pAp", "update_xr(K2)", "reduce_rr", "update_p(K3)",
-                                        "halo_push", "residual_init", "reduce_rr0"], [round(v, 4) for v in phase_sum])),
+               "schedule": "deferred-x (4 launches, 112 B/row per iteration)" if deferred_x
+               else "classic (5 launches, 128 B/row per iteration)",
+               "iter_bytes_model": iter_bytes, "solve_bytes_model": solve_bytes,
+               "solve_gb_s": solve_bytes / (ms * 1e-3) / 1e9},
+        "phases_ms_per_step": dict(zip(["_", "spmv(K1/K1F)", "reduce_pAp", "update_r(K2r)" if deferred_x else "update_xr(K2)",
+                                        "reduce_rr", "finish_x" if deferred_x else "update_p(K3)",
+                                        "halo_dir" if deferred_x else "halo_push", "residual_init", "reduce_rr0"],
+                                       [round(v, 4) for v in phase_sum])),
         "clocks": clocks,
     }
     if world == 1 and not args.no_operators:

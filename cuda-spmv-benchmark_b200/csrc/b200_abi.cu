@@ -53,7 +53,7 @@ struct Variant {
 };
 // keep in sync with the dispatch switch below
 const Variant kVariants[] = {
-    {2, 2, 3, "v0 (default): 64-col strips (2 cols/lane), 2 warps/CTA, 3-stage ring"},
+    {4, 4, 2, "v0 (default): 128-col strips (4 cols/lane), 4 warps/CTA, 2-stage ring"},
     {1, 4, 4, "v1: 32-col strips (1 col/lane), 4 warps/CTA, 4-stage ring"},
     {2, 8, 4, "v2: 64-col strips, 8 warps/CTA, 4-stage ring"},
     {4, 4, 3, "v3: 128-col strips (4 cols/lane), 4 warps/CTA, 3-stage ring"},
@@ -62,12 +62,14 @@ const Variant kVariants[] = {
     {4, 2, 3, "v6: 128-col strips, 2 warps/CTA, 3-stage ring"},
     {2, 4, 4, "v7: 64-col strips, 4 warps/CTA, 4-stage ring"},
     {2, 1, 4, "v8: 64-col strips, 1 warp/CTA, 4-stage ring"},
-    {4, 4, 2, "v9: 128-col strips, 4 warps/CTA, 2-stage ring"},
+    {2, 2, 3, "v9: 64-col strips (2 cols/lane), 2 warps/CTA, 3-stage ring (round-1 default until the K1F sweep)"},
     {4, 1, 3, "v10: 128-col strips, 1 warp/CTA, 3-stage ring"},
     {2, 4, 2, "v11: 64-col strips, 4 warps/CTA, 2-stage ring"},
+    {4, 8, 2, "v12: 128-col strips, 8 warps/CTA, 2-stage ring"},
+    {4, 2, 2, "v13: 128-col strips, 2 warps/CTA, 2-stage ring"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-const int kDefaultRowsPerItem = 16;
+const int kDefaultRowsPerItem = 8;
 
 struct Geometry {
     Stencil5Args a;
@@ -164,10 +166,12 @@ int launch_variant(int v, const Geometry& g, cudaStream_t s) {
         case 6: return launch_one<MODE, 4, 2, 3, CG>(g, s);
         case 7: return launch_one<MODE, 2, 4, 4, CG>(g, s);
         case 8: return launch_one<MODE, 2, 1, 4, CG>(g, s);
-        case 9: return launch_one<MODE, 4, 4, 2, CG>(g, s);
+        case 9: return launch_one<MODE, 2, 2, 3, CG>(g, s);
         case 10: return launch_one<MODE, 4, 1, 3, CG>(g, s);
         case 11: return launch_one<MODE, 2, 4, 2, CG>(g, s);
-        default: return launch_one<MODE, 2, 2, 3, CG>(g, s);
+        case 12: return launch_one<MODE, 4, 8, 2, CG>(g, s);
+        case 13: return launch_one<MODE, 4, 2, 2, CG>(g, s);
+        default: return launch_one<MODE, 4, 4, 2, CG>(g, s);
     }
 }
 
@@ -505,6 +509,92 @@ extern "C" int b200_cg_update_p_push(long long n, const void* d_scalars, const d
     const int grid = blas1_grid(n, 1);
     cg_update_p_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, a.sc, d_r, d_p, a);
     return check_launch("cg_update_p_push_kernel");
+}
+
+extern "C" int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
+                                  double* d_x, double* d_Ap, double* d_partials, const void* d_scalars,
+                                  b200_stream stream) {
+    Geometry g;
+    int rc = build_geometry(band, d_p_old, &g);
+    if (rc) return rc;
+    if (!d_r || !d_p_new || !d_x || !d_Ap || !d_partials || !d_scalars) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
+    if (d_p_new == d_p_old) return fail(B200_EINVAL, "cg_spmv_fused: p_new must not alias p_old");
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    g.a.y = d_Ap; g.a.y2 = d_p_new; g.a.r = d_r; g.a.xs = d_x; g.a.partials = d_partials;
+    g.a.ab = &sc->alpha;
+    static_assert(offsetof(CGScalars, beta) == offsetof(CGScalars, alpha) + sizeof(double), "alpha, beta adjacent");
+    g.a.converged = &sc->converged;
+    g.a.error_word = &const_cast<CGScalars*>(sc)->error;
+    return launch_stencil<ST_FUSED>(band, g, (cudaStream_t)stream);
+}
+
+namespace {
+int launch_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r, double* d_partials,
+                    int* n_partials_out, const HaloPushArgs* h, cudaStream_t s) {
+    const bool v2 = aligned16(d_Ap) && aligned16(d_r);
+    const int grid = blas1_grid(n, v2 ? 2 : 1);
+    if (n_partials_out) *n_partials_out = grid;
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    HaloPushArgs none;
+    memset(&none, 0, sizeof none);
+    if (h) {
+        if (v2) cg_update_r_kernel<2, true><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, *h);
+        else cg_update_r_kernel<1, true><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, *h);
+    } else {
+        if (v2) cg_update_r_kernel<2, false><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, none);
+        else cg_update_r_kernel<1, false><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, none);
+    }
+    return check_launch("cg_update_r_kernel");
+}
+}  // namespace
+
+extern "C" int b200_cg_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
+                                double* d_partials, int* n_partials_out, b200_stream stream) {
+    if (!d_scalars || !d_Ap || !d_r || !d_partials) return fail(B200_EINVAL, "cg_update_r: NULL argument");
+    return launch_update_r(n, d_scalars, d_Ap, d_r, d_partials, n_partials_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200_cg_update_r_push(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
+                                     double* d_partials, int* n_partials_out, int halo, double* d_dst_prev,
+                                     double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next,
+                                     uint32_t epoch, void* d_my_xchg, b200_stream stream) {
+    if (!d_scalars || !d_Ap || !d_r || !d_partials || !d_my_xchg || halo < 1 || n < halo)
+        return fail(B200_EINVAL, "cg_update_r_push: bad argument");
+    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "cg_update_r_push: NULL flag");
+    HaloPushArgs a;
+    a.v_local = d_r; a.n_local = n; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
+    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
+    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
+    a.sc = static_cast<const CGScalars*>(d_scalars);
+    return launch_update_r(n, d_scalars, d_Ap, d_r, d_partials, n_partials_out, &a, (cudaStream_t)stream);
+}
+
+extern "C" int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const double* d_pold_prev,
+                                const double* d_pold_next, double* d_pnew_prev, double* d_pnew_next, int halo,
+                                const uint32_t* d_flag_prev, const uint32_t* d_flag_next, uint32_t epoch,
+                                void* d_scalars, int beta_zero, b200_stream stream) {
+    if (!d_scalars || halo < 1) return fail(B200_EINVAL, "cg_halo_dir: bad argument");
+    if ((d_r_prev && (!d_pnew_prev || !d_flag_prev || (!beta_zero && !d_pold_prev))) ||
+        (d_r_next && (!d_pnew_next || !d_flag_next || (!beta_zero && !d_pold_next))))
+        return fail(B200_EINVAL, "cg_halo_dir: NULL buffer");
+    if (!d_r_prev && !d_r_next) return B200_OK;
+    HaloDirArgs a;
+    a.r_prev = d_r_prev; a.r_next = d_r_next; a.pold_prev = d_pold_prev; a.pold_next = d_pold_next;
+    a.pnew_prev = d_pnew_prev; a.pnew_next = d_pnew_next; a.halo = halo;
+    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
+    a.sc = static_cast<CGScalars*>(d_scalars); a.beta_zero = beta_zero;
+    int grid = (halo + 255) / 256;
+    if (grid > 64) grid = 64;
+    cg_halo_dir_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("cg_halo_dir_kernel");
+}
+
+extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
+                                double* d_x, b200_stream stream) {
+    if (!d_scalars || !d_p0 || !d_p1 || !d_x) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    cg_finish_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x);
+    return check_launch("cg_finish_x_kernel");
 }
 
 extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,

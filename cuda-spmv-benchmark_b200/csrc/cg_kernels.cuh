@@ -50,6 +50,20 @@ struct XchgArea {
     uint32_t pad[26];
 };
 
+// arguments of the kernels that push halo elements into the neighbours' landing buffers
+struct HaloPushArgs {
+    const double* v_local;
+    long long n_local;
+    int halo;
+    double* dst_prev;  // rank-1's halo_next landing buffer (NULL if rank == 0)
+    double* dst_next;  // rank+1's halo_prev landing buffer (NULL if last rank)
+    uint32_t* flag_prev;  // rank-1's halo_flag_next
+    uint32_t* flag_next;  // rank+1's halo_flag_prev
+    uint32_t epoch;
+    uint32_t* push_count;  // my_xchg->push_count
+    const CGScalars* sc;
+};
+
 enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3 };
 enum { RED_PUSH = 1, RED_COMBINE = 2 };
 
@@ -227,6 +241,144 @@ __global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CG
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// ---- "deferred x" schedule (4 launches, 112 B/row per iteration instead of 5 launches, 128 B/row) -------
+// The stencil kernel in ST_FUSED mode forms p = r + beta p_old while it loads the rows, retires
+// x += alpha_prev p_old on the way and writes the new p once (stencil5.cuh).  What is left of K2 is
+//   K2r: r -= alpha Ap ; partials r.r     (24 B/row; the p and x streams of K2 are gone)
+// with the SAME tiling and summation order as cg_update_xr_kernel, so r.r -- and with it alpha, beta
+// and every iterate -- is bit-identical to the classic schedule.  Multi-GPU (PUSH): the CTAs that
+// produce the first / last `halo` elements of r store them straight into the neighbours' landing
+// buffers over NVLink; the last CTA publishes the arrival epoch (as cg_update_p_push_kernel does for p).
+template <int VEC, bool PUSH>
+__global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                          const double* __restrict__ Ap, double* __restrict__ r,
+                                                          double* __restrict__ partials, const HaloPushArgs h) {
+    __shared__ double scratch[8];
+    if (sc->converged) return;
+    const double nalpha = -sc->alpha;
+    constexpr int UNROLL = 4;
+    const long long tile = 256LL * VEC * UNROLL;
+    const long long next_lo = n - h.halo;
+    auto push = [&](long long i, double v) {
+        if (PUSH) {
+            if (h.dst_prev != nullptr && i < h.halo) h.dst_prev[i] = v;
+            if (h.dst_next != nullptr && i >= next_lo) h.dst_next[i - next_lo] = v;
+        }
+    };
+    double acc = 0.0;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        if (VEC == 2) {
+            double2 av[UNROLL], rv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    av[u] = __ldcs(reinterpret_cast<const double2*>(Ap + i));
+                    rv[u] = __ldcs(reinterpret_cast<const double2*>(r + i));
+                } else if (i < n) {
+                    av[u] = make_double2(Ap[i], 0.0);
+                    rv[u] = make_double2(r[i], 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i < n) {
+                    rv[u].x = fma(nalpha, av[u].x, rv[u].x);
+                    acc = fma(rv[u].x, rv[u].x, acc);
+                    push(i, rv[u].x);
+                    if (i + 1 < n) {
+                        rv[u].y = fma(nalpha, av[u].y, rv[u].y);
+                        acc = fma(rv[u].y, rv[u].y, acc);
+                        push(i + 1, rv[u].y);
+                        *reinterpret_cast<double2*>(r + i) = rv[u];
+                    } else {
+                        r[i] = rv[u].x;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + (long long)u * 256 + threadIdx.x;
+                if (i < n) {
+                    const double rn = fma(nalpha, Ap[i], r[i]);
+                    r[i] = rn;
+                    acc = fma(rn, rn, acc);
+                    push(i, rn);
+                }
+            }
+        }
+    }
+    if (PUSH) __threadfence_system();
+    acc = block_sum(acc, scratch);  // contains a __syncthreads
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = acc;
+        if (PUSH) {
+            const uint32_t done = atomicAdd(&h.push_count[0], 1u) + 1u;
+            if (done == gridDim.x) {
+                h.push_count[0] = 0;
+                __threadfence_system();
+                if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, h.epoch);
+                if (h.dst_next != nullptr) st_release_sys(h.flag_next, h.epoch);
+            }
+        }
+    }
+}
+
+// Halo part of the direction update (multi-GPU, deferred-x schedule): the neighbours pushed the edges
+// of their NEW r; the halo copies of p follow the same recurrence as the local part,
+// p_halo = fma(beta, p_halo_old, r_halo), kept in two local ping-pong buffers.  beta_zero: first
+// direction (p0 = r0).  One small CTA group; waits (bounded) for the arrival epochs first.
+struct HaloDirArgs {
+    const double* r_prev;  // landing buffers written by the neighbours (NULL at the ends)
+    const double* r_next;
+    const double* pold_prev;
+    const double* pold_next;
+    double* pnew_prev;
+    double* pnew_next;
+    int halo;
+    const uint32_t* flag_prev;
+    const uint32_t* flag_next;
+    uint32_t epoch;
+    CGScalars* sc;
+    int beta_zero;
+};
+
+__global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
+    if (a.sc->converged) return;
+    if (threadIdx.x == 0) {
+        const uint64_t t0 = globaltimer_ns();
+        const uint32_t* fl[2] = {a.r_prev ? a.flag_prev : nullptr, a.r_next ? a.flag_next : nullptr};
+        for (int d = 0; d < 2; d++) {
+            if (!fl[d]) continue;
+            while ((int32_t)(ld_acquire_sys(fl[d]) - a.epoch) < 0) {
+                if (a.sc->error || globaltimer_ns() - t0 > 8000000000ull) { a.sc->error = 1; break; }
+                __nanosleep(64);
+            }
+        }
+    }
+    __syncthreads();
+    const double beta = a.beta_zero ? 0.0 : a.sc->beta;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < a.halo; i += gridDim.x * 256) {
+        if (a.r_prev) a.pnew_prev[i] = a.beta_zero ? __ldcg(a.r_prev + i) : fma(beta, a.pold_prev[i], __ldcg(a.r_prev + i));
+        if (a.r_next) a.pnew_next[i] = a.beta_zero ? __ldcg(a.r_next + i) : fma(beta, a.pold_next[i], __ldcg(a.r_next + i));
+    }
+}
+
+// After the last iteration of the deferred-x schedule x still lacks alpha_last * p_last.
+// p_last lives in p0 or p1 depending on the parity of the completed iterations (known on the device).
+__global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                          const double* __restrict__ p0,
+                                                          const double* __restrict__ p1, double* __restrict__ x) {
+    const int it = sc->iterations;
+    if (it <= 0) return;
+    const double alpha = sc->alpha;
+    const double* __restrict__ p = ((it - 1) & 1) ? p1 : p0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        x[i] = fma(alpha, p[i], x[i]);
+}
+
 // K3: p = r + beta p   (reference update_p_kernel, cg_solver.cu:91-96: fma(beta,p,r))
 template <int VEC>
 __global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
@@ -336,18 +488,6 @@ __global__ void __launch_bounds__(256) checksum_partials_kernel(long long n, con
 // neighbours' landing buffers over NVLink (peer stores), followed by a release-store of the epoch
 // into the neighbour's flag.  Replaces exchange_halo_mpi (cg_solver_mgpu_partitioned.cu:173-231:
 // D2H, MPI_Isend/Irecv, H2D, two stream syncs).  gridDim.x = 2 * ctas_per_dir.
-struct HaloPushArgs {
-    const double* v_local;
-    long long n_local;
-    int halo;
-    double* dst_prev;  // rank-1's halo_next landing buffer (NULL if rank == 0)
-    double* dst_next;  // rank+1's halo_prev landing buffer (NULL if last rank)
-    uint32_t* flag_prev;  // rank-1's halo_flag_next
-    uint32_t* flag_next;  // rank+1's halo_flag_prev
-    uint32_t epoch;
-    uint32_t* push_count;  // my_xchg->push_count
-    const CGScalars* sc;
-};
 
 __global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
     if (a.sc != nullptr && a.sc->converged) return;

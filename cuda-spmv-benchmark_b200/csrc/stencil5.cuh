@@ -17,7 +17,9 @@
 //     once per item (coalesced 256 B per warp), west/east come from neighbouring lanes by shuffle.
 //   * Boundary rows of the grid (4n-4 rows) walk the CSR arrays in extra CTAs at the end of the
 //     same launch.
-//   * Optional fusion (template MODE): p.Ap partial sums (CG), or r = b - A x, p = r, r.r.
+//   * Optional fusion (template MODE): p.Ap partial sums (CG), or r = b - A x, p = r, r.r, or the
+//     whole direction update (ST_FUSED): p = r + beta p_old is formed in registers while the rows
+//     are loaded, written once, x += alpha p_old is retired on the way, then Ap = A p and p.Ap.
 //   * Band mode (multi-GPU): x is addressed as local / halo_prev / halo_next exactly like the
 //     reference halo kernel; items that touch a halo spin on the neighbour's arrival flag, and are
 //     scheduled last so the halo transfer overlaps the interior work.
@@ -28,7 +30,7 @@
 
 namespace b200 {
 
-enum { ST_PLAIN = 0, ST_DOT = 1, ST_RESID = 2 };
+enum { ST_PLAIN = 0, ST_DOT = 1, ST_RESID = 2, ST_FUSED = 3 };
 
 struct Stencil5Args {
     const int* row_ptr;    // local, rebased to 0 (boundary rows only)
@@ -60,6 +62,10 @@ struct Stencil5Args {
     uint32_t epoch;
     const int* converged;  // optional: kernel is a no-op once *converged != 0
     int* error_word;       // optional: set to 1 on a flag-wait timeout
+    // ST_FUSED: x = p_old (local part; the halos hold the NEW p), y = Ap, y2 = p_new
+    const double* r;       // residual (local)
+    double* xs;            // solution vector: xs += alpha * p_old
+    const double* ab;      // device scalars: ab[0] = alpha (of the previous iteration), ab[1] = beta
 };
 
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, int* error_word) {
@@ -74,10 +80,19 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, 
     }
 }
 
-template <bool CG_LOADS>
-__device__ __forceinline__ double x_at(const Stencil5Args& a, long long idx) {
+// Vector element `idx` (local index; outside [0, n_local) = halo).  ST_FUSED: the local part is
+// formed on the fly, p = fma(beta, p_old, r) (reference update_p_kernel, cg_solver.cu:91-96), the
+// halos already hold the new p.  `po` receives p_old (0 outside the band).
+template <int MODE, bool CG_LOADS>
+__device__ __forceinline__ double x_at(const Stencil5Args& a, long long idx, double beta = 0.0, double* po = nullptr) {
     const double* p;
+    if (MODE == ST_FUSED && po) *po = 0.0;
     if (idx >= 0 && idx < a.n_local) {
+        if (MODE == ST_FUSED) {
+            const double pold = __ldg(a.x + idx);
+            if (po) *po = pold;
+            return fma(beta, pold, __ldg(a.r + idx));
+        }
         p = a.x + idx;
     } else if (idx < 0) {
         if (a.halo_prev == nullptr || idx < -(long long)a.n) return 0.0;
@@ -91,7 +106,7 @@ __device__ __forceinline__ double x_at(const Stencil5Args& a, long long idx) {
 
 // One boundary row: CSR walk, reference order (spmv_stencil_csr_direct.cu:113-119).
 template <int MODE, bool CG_LOADS>
-__device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long r) {
+__device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long r, double alpha, double beta) {
     const long long lr = r - a.row_offset;
     long long s, e;
     if (a.row_ptr != nullptr) { s = a.row_ptr[lr]; e = a.row_ptr[lr + 1]; }
@@ -100,9 +115,17 @@ __device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long 
     for (long long k = s; k < e; k++) {
         const long long c = a.col_idx[k];
         if (c < 0) continue;
-        const double xv = x_at<CG_LOADS>(a, c - a.row_offset);
+        const double xv = x_at<MODE, CG_LOADS>(a, c - a.row_offset, beta);
         if (c == r) xc = xv;
         sum = fma(a.values[k], xv, sum);
+    }
+    if (MODE == ST_FUSED) {  // this thread owns row r: retire x, publish the new p
+        const double pold = a.x[lr];
+        xc = fma(beta, pold, a.r[lr]);
+        a.y2[lr] = xc;
+        a.xs[lr] = fma(alpha, pold, a.xs[lr]);
+        a.y[lr] = sum;
+        return xc * sum;
     }
     if (MODE == ST_RESID) {
         const double rv = a.b[lr] - sum;
@@ -125,6 +148,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
+    const double alpha = (MODE == ST_FUSED) ? a.ab[0] : 0.0, beta = (MODE == ST_FUSED) ? a.ab[1] : 0.0;
 
     if ((int)blockIdx.x >= a.n_interior_ctas) {
         // ------------------------------------------------------------ boundary pass (CSR walk)
@@ -143,7 +167,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
             else if (t < 2LL * n) r = (long long)(n - 1) * n + (t - n);    // grid row n-1
             else if (t < 2LL * n + (n - 2)) r = (t - 2LL * n + 1) * n;     // column 0
             else r = (t - 2LL * n - (n - 2) + 1) * n + (n - 1);            // column n-1
-            if (r >= a.row_offset && r < a.row_offset + a.n_local) acc = boundary_row<MODE, CG_LOADS>(a, r);
+            if (r >= a.row_offset && r < a.row_offset + a.n_local) acc = boundary_row<MODE, CG_LOADS>(a, r, alpha, beta);
         }
     } else {
         // ------------------------------------------------------------ interior fast path
@@ -161,8 +185,10 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
         int chunk = blockIdx.x / a.ctas_per_chunk;
         const int strip = (blockIdx.x % a.ctas_per_chunk) * WARPS + warp;
         const bool halo_mode = (a.flag_prev != nullptr || a.flag_next != nullptr);
-        if (halo_mode && a.n_chunks >= 3) {
+        if ((halo_mode || a.halo_prev != nullptr || a.halo_next != nullptr) && a.n_chunks >= 3) {
             // chunks that read a halo (first / last of the band) run last: transfer overlaps the rest
+            // (keyed on the halo pointers as well, so that the CTA -> item map, and with it the order
+            // of the partial sums, does not depend on whether the launch has to wait for flags)
             chunk = (chunk < a.n_chunks - 2) ? chunk + 1 : (chunk == a.n_chunks - 2 ? 0 : a.n_chunks - 1);
         }
         const int i0 = a.i_first + chunk * a.rows_per_item;
@@ -229,24 +255,65 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
             // stalls on global-memory latency (only on the values ring).
             double xN[COLS], xC[COLS], xS[COLS], xF[COLS] = {};
             double eC = 0.0, eS = 0.0, eF = 0.0;  // lane 0: x(i, j0-1)   lane 31: x(i, j0+W)
+            // ST_FUSED: xF / eF hold the raw r of the row in flight (or the halo's new p), poF / peF its
+            // p_old; the row becomes p = fma(beta, p_old, r) one turn later, when the loads have
+            // landed.  poS / poC carry p_old down to the turn that retires x += alpha p_old.
+            double poF[COLS] = {}, poS[COLS] = {}, poC[COLS] = {};
+            double peF = 0.0;
             const long long col_base = (long long)j0 + lane - off;  // + i*n + 32c -> local index
-            auto load_row = [&](int ii, double (&xr)[COLS], double& er) {
+            auto raw_at = [&](long long idx, double& po) -> double {  // (r or halo p, p_old): no arithmetic
+                po = 0.0;
+                if (idx >= 0 && idx < nl) {
+                    po = __ldg(a.x + idx);
+                    return __ldg(a.r + idx);
+                }
+                return x_at<ST_PLAIN, CG_LOADS>(a, idx);
+            };
+            auto load_row = [&](int ii, double (&xr)[COLS], double& er, double (&po)[COLS], double& pe) {
                 const long long rb = (long long)ii * n;
 #pragma unroll
                 for (int c = 0; c < COLS; c++) {
                     const int j = j0 + lane + 32 * c;
-                    xr[c] = (j <= n - 1) ? x_at<CG_LOADS>(a, rb + col_base + 32 * c) : 0.0;
+                    po[c] = 0.0;
+                    if (MODE == ST_FUSED) xr[c] = (j <= n - 1) ? raw_at(rb + col_base + 32 * c, po[c]) : 0.0;
+                    else xr[c] = (j <= n - 1) ? x_at<MODE, CG_LOADS>(a, rb + col_base + 32 * c) : 0.0;
                 }
                 er = 0.0;
-                if (lane == 0) er = x_at<CG_LOADS>(a, rb + j0 - 1 - off);
-                if (lane == 31 && j0 + W <= n - 1) er = x_at<CG_LOADS>(a, rb + j0 + W - off);
+                pe = 0.0;
+                if (MODE == ST_FUSED) {
+                    if (lane == 0) er = raw_at(rb + j0 - 1 - off, pe);
+                    if (lane == 31 && j0 + W <= n - 1) er = raw_at(rb + j0 + W - off, pe);
+                } else {
+                    if (lane == 0) er = x_at<MODE, CG_LOADS>(a, rb + j0 - 1 - off);
+                    if (lane == 31 && j0 + W <= n - 1) er = x_at<MODE, CG_LOADS>(a, rb + j0 + W - off);
+                }
+            };
+            auto finish_row = [&](double (&xr)[COLS], double& er, const double (&po)[COLS], double pe) {
+                if (MODE == ST_FUSED) {  // raw -> p = fma(beta, p_old, r); halo / padding: fma(beta, 0, v) = v
+#pragma unroll
+                    for (int c = 0; c < COLS; c++) xr[c] = fma(beta, po[c], xr[c]);
+                    er = fma(beta, pe, er);
+                }
             };
             {
-                double dummy;
-                load_row(i0 - 1, xN, dummy);
+                double dummy, dpe, dpo[COLS];
+                load_row(i0 - 1, xN, dummy, dpo, dpe);
+                finish_row(xN, dummy, dpo, dpe);
             }
-            load_row(i0, xC, eC);
-            load_row(i0 + 1, xS, eS);
+            {
+                double dpe;
+                load_row(i0, xC, eC, poC, dpe);
+                finish_row(xC, eC, poC, dpe);
+            }
+            load_row(i0 + 1, xS, eS, poS, peF);
+            if (MODE != ST_FUSED) {
+                // nothing: xS is final
+            } else {
+                // keep row i0+1 raw in the F registers: it is finished at the top of the first turn
+#pragma unroll
+                for (int c = 0; c < COLS; c++) { xF[c] = xS[c]; poF[c] = poS[c]; }
+                eF = eS;
+            }
 
             uint32_t phase_bits = 0;
             for (int i = i0; i < i1; i++) {
@@ -254,7 +321,23 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 __syncwarp();
                 if (i + STAGES - 1 < i1) issue(i + STAGES - 1);
 
-                if (i + 2 <= i1) load_row(i + 2, xF, eF);
+                double xsv[COLS];
+                if (MODE == ST_FUSED) {
+                    // row i+1 was loaded one turn ago: finish it, then reuse the F registers for row i+2
+#pragma unroll
+                    for (int c = 0; c < COLS; c++) { xS[c] = xF[c]; poS[c] = poF[c]; }
+                    eS = eF;
+                    finish_row(xS, eS, poS, peF);
+                    if (i + 2 <= i1) load_row(i + 2, xF, eF, poF, peF);
+#pragma unroll
+                    for (int c = 0; c < COLS; c++) {
+                        const long long r = (long long)i * n + j0 + lane + 32 * c;
+                        xsv[c] = (j0 + lane + 32 * c <= n - 2 && r >= off && r < off + nl) ? a.xs[r - off] : 0.0;
+                    }
+                } else {
+                    double dpo[COLS], dpe;
+                    if (i + 2 <= i1) load_row(i + 2, xF, eF, dpo, dpe);
+                }
                 double bv[COLS];
                 if (MODE == ST_RESID) {
 #pragma unroll
@@ -313,15 +396,25 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                                 acc = fma(rv, rv, acc);
                             } else {
                                 a.y[lr] = t;
-                                if (MODE == ST_DOT) acc = fma(xC[c], t, acc);
+                                if (MODE == ST_DOT || MODE == ST_FUSED) acc = fma(xC[c], t, acc);
+                                if (MODE == ST_FUSED) {
+                                    a.y2[lr] = xC[c];                          // the new p, written once
+                                    a.xs[lr] = fma(alpha, poC[c], xsv[c]);     // x += alpha p_old, deferred
+                                }
                             }
                         }
                     }
                 }
+                if (MODE == ST_FUSED) {
 #pragma unroll
-                for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; xS[c] = xF[c]; }
-                eC = eS;
-                eS = eF;
+                    for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; poC[c] = poS[c]; }
+                    eC = eS;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; xS[c] = xF[c]; }
+                    eC = eS;
+                    eS = eF;
+                }
             }
         }
     }

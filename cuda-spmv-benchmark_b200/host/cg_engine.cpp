@@ -66,9 +66,12 @@ struct Mgpu {
     bool single_device = true;  // all local ranks on one device: split reduce launches
 } g;
 
-size_t block_bytes() { return g.area_bytes + 2 * g.halo_cap * sizeof(double); }
+// block = exchange area | landing_prev | landing_next (written by the neighbours) | 4 local buffers:
+// halo copies of the search direction, [parity][prev / next] (deferred-x schedule)
+size_t block_bytes() { return g.area_bytes + 6 * g.halo_cap * sizeof(double); }
 double* landing_prev(int r) { return reinterpret_cast<double*>(static_cast<char*>(g.xchg[r]) + g.area_bytes); }
 double* landing_next(int r) { return landing_prev(r) + g.halo_cap; }
+double* halo_dir(int r, int parity, int next) { return landing_prev(r) + (2 + 2 * (parity & 1) + (next ? 1 : 0)) * g.halo_cap; }
 uint32_t* flag_prev(int r) { return reinterpret_cast<uint32_t*>(static_cast<char*>(g.xchg[r]) + b200_xchg_flag_prev_offset()); }
 uint32_t* flag_next(int r) { return reinterpret_cast<uint32_t*>(static_cast<char*>(g.xchg[r]) + b200_xchg_flag_next_offset()); }
 
@@ -94,6 +97,8 @@ int alloc_block(int dev, void** out) {
 
 }  // namespace
 
+namespace { extern int g_schedule; }
+extern "C" void b200_cg_set_schedule(int deferred_x) { g_schedule = deferred_x ? 1 : 0; }
 extern "C" int b200_mgpu_world(void) { return g.inited ? g.world : 1; }
 extern "C" int b200_mgpu_rank(void) { return (g.inited && g.nlocal == 1) ? g.local_rank[0] : 0; }
 extern "C" void b200_mgpu_finalize(void) { mgpu_reset(); }
@@ -174,7 +179,7 @@ struct RankWs {
     bool own_stream = false;
     DeviceBand band;
     bool own_band = false;
-    double *x = nullptr, *r = nullptr, *p = nullptr, *Ap = nullptr, *b = nullptr;
+    double *x = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *Ap = nullptr, *b = nullptr;
     double *partials = nullptr, *partials2 = nullptr, *stash = nullptr, *sums = nullptr;
     void* scalars = nullptr;
     HostStatus* status = nullptr;  // pinned + mapped
@@ -186,9 +191,9 @@ struct RankWs {
     std::vector<cudaEvent_t> phase_ev;  // detailed timers
 
     void free_vectors() {
-        cudaFree(x); cudaFree(r); cudaFree(p); cudaFree(Ap); cudaFree(b);
+        cudaFree(x); cudaFree(r); cudaFree(p); cudaFree(p2); cudaFree(Ap); cudaFree(b);
         cudaFree(partials); cudaFree(partials2); cudaFree(stash); cudaFree(sums); cudaFree(scalars);
-        x = r = p = Ap = b = partials = partials2 = stash = sums = nullptr;
+        x = r = p = p2 = Ap = b = partials = partials2 = stash = sums = nullptr;
         scalars = nullptr;
         if (status) cudaFreeHost((void*)status);
         status = nullptr;
@@ -225,6 +230,7 @@ int alloc_rank_vectors(RankWs& w, int max_partials) {
     B200_CUDA(cudaMalloc(&w.x, vb));
     B200_CUDA(cudaMalloc(&w.r, vb));
     B200_CUDA(cudaMalloc(&w.p, vb));
+    B200_CUDA(cudaMalloc(&w.p2, vb));  // second direction buffer (deferred-x schedule)
     B200_CUDA(cudaMalloc(&w.Ap, vb));
     B200_CUDA(cudaMalloc(&w.b, vb));
     w.max_partials = max_partials;
@@ -283,6 +289,27 @@ void wire_band(const RankWs& w, b200_band* b, bool halos, uint32_t epoch) {
         if (w.rank < g.world - 1) { b->d_halo_next = landing_next(w.rank); b->d_flag_next = flag_next(w.rank); }
         b->epoch = epoch;
     }
+}
+
+// band descriptor whose halos are the local direction copies of the given parity (no flags: the
+// halo-direction kernel has already waited for the neighbours)
+void wire_band_dir(const RankWs& w, b200_band* b, int parity) {
+    w.band.describe(b);
+    if (g.world > 1) {
+        if (w.rank > 0) b->d_halo_prev = halo_dir(w.rank, parity, 0);
+        if (w.rank < g.world - 1) b->d_halo_next = halo_dir(w.rank, parity, 1);
+    }
+}
+
+// deferred-x schedule (4 launches, 112 B/row per iteration) unless B200_CG_SCHEDULE=classic or
+// b200_cg_set_schedule(0)
+int g_schedule = -1;
+bool schedule_deferred_x() {
+    if (g_schedule < 0) {
+        const char* e = getenv("B200_CG_SCHEDULE");
+        g_schedule = (e && strcmp(e, "classic") == 0) ? 0 : 1;
+    }
+    return g_schedule == 1;
 }
 
 int push_halo(const RankWs& w, const double* v, uint32_t epoch, const void* scalars) {
@@ -390,18 +417,56 @@ struct Engine {
 
         // ---- iterations (cg_solver.cu:538-638)
         const int lag = verbose >= 2 ? 0 : kLag;
+        const bool dx = fused && schedule_deferred_x();
+        if (multi && dx) {
+            // first direction: p0 = r0, its edges are in the landing buffers (pushed above)
+            for (auto& w : ws.ranks) {
+                B200_CUDA(cudaSetDevice(w.dev));
+                B200_K(b200_cg_halo_dir(w.rank > 0 ? landing_prev(w.rank) : nullptr,
+                                        w.rank < g.world - 1 ? landing_next(w.rank) : nullptr, nullptr, nullptr,
+                                        halo_dir(w.rank, 0, 0), halo_dir(w.rank, 0, 1), ws.grid, flag_prev(w.rank),
+                                        flag_next(w.rank), g.halo_epoch, w.scalars, 1, w.st));
+            }
+            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
+            pt.mark(T_HALO);
+        }
         const size_t loop_mark0 = pt.used;            // first phase mark of the iteration loop
-        const size_t marks_per_iter = 5;              // K1, R, K2, R, K3 (halo push fused into K3)
+        // classic: K1, R, K2, R, K3 (halo push fused into K3); deferred x: [H,] K1F, R, K2r, R
+        const size_t marks_per_iter = dx ? (multi ? 5 : 4) : 5;
         int launched = 0;
         bool done = false;
         Nvtx range_solver("CG_Solver");
         for (int it = 0; it < max_iters && !done; it++) {
             Nvtx range_iter("CG_Iteration");
+            if (dx && multi) {
+                // halo copies of the new direction (it >= 1): p_halo = r_halo + beta p_halo_old
+                Nvtx range_h("Halo_Direction");
+                for (auto& w : ws.ranks) {
+                    B200_CUDA(cudaSetDevice(w.dev));
+                    if (it >= 1)
+                        B200_K(b200_cg_halo_dir(w.rank > 0 ? landing_prev(w.rank) : nullptr,
+                                                w.rank < g.world - 1 ? landing_next(w.rank) : nullptr,
+                                                halo_dir(w.rank, it - 1, 0), halo_dir(w.rank, it - 1, 1),
+                                                halo_dir(w.rank, it, 0), halo_dir(w.rank, it, 1), ws.grid,
+                                                flag_prev(w.rank), flag_next(w.rank), g.halo_epoch, w.scalars, 0, w.st));
+                }
+                B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
+                pt.mark(T_HALO);
+            }
             nvtxRangePushA("SpMV");
             for (size_t l = 0; l < L; l++) {  // K1: Ap = A p, partials p.Ap
                 RankWs& w = ws.ranks[l];
                 B200_CUDA(cudaSetDevice(w.dev));
-                if (fused) {
+                if (dx) {
+                    // direction k lives in p (k even) or p2 (k odd)
+                    double* pcur = (it & 1) ? w.p2 : w.p;
+                    double* pold = (it & 1) ? w.p : w.p2;
+                    b200_band band;
+                    wire_band_dir(w, &band, it);
+                    if (it == 0) B200_K(b200_cg_spmv_dot(&band, pcur, w.Ap, w.partials, w.scalars, w.st));
+                    else B200_K(b200_cg_spmv_fused(&band, pold, w.r, pcur, w.x, w.Ap, w.partials, w.scalars, w.st));
+                    np[l] = n_partials_spmv[l];
+                } else if (fused) {
                     b200_band band;
                     wire_band(w, &band, true, g.halo_epoch);
                     B200_K(b200_cg_spmv_dot(&band, w.p, w.Ap, w.partials, w.scalars, w.st));
@@ -420,10 +485,30 @@ struct Engine {
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_RED_PAP);
             nvtxRangePushA("BLAS_AXPY");
-            for (size_t l = 0; l < L; l++) {  // K2: x += alpha p, r -= alpha Ap, partials r.r
-                RankWs& w = ws.ranks[l];
-                B200_CUDA(cudaSetDevice(w.dev));
-                B200_K(b200_cg_update_xr(w.nl, w.scalars, w.p, w.Ap, w.x, w.r, w.partials2, &np[l], w.st));
+            if (dx) {
+                // K2r: r -= alpha Ap, partials r.r; multi-GPU: the edges of the new r go straight into
+                // the neighbours' landing buffers, the last CTA publishes the arrival epoch
+                const uint32_t e = multi ? ++g.halo_epoch : 0;
+                for (size_t l = 0; l < L; l++) {
+                    RankWs& w = ws.ranks[l];
+                    B200_CUDA(cudaSetDevice(w.dev));
+                    if (multi) {
+                        double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
+                        double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
+                        uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
+                        uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
+                        B200_K(b200_cg_update_r_push(w.nl, w.scalars, w.Ap, w.r, w.partials2, &np[l], ws.grid, dprev, dnext,
+                                                     fprev, fnext, e, g.xchg[w.rank], w.st));
+                    } else {
+                        B200_K(b200_cg_update_r(w.nl, w.scalars, w.Ap, w.r, w.partials2, &np[l], w.st));
+                    }
+                }
+            } else {
+                for (size_t l = 0; l < L; l++) {  // K2: x += alpha p, r -= alpha Ap, partials r.r
+                    RankWs& w = ws.ranks[l];
+                    B200_CUDA(cudaSetDevice(w.dev));
+                    B200_K(b200_cg_update_xr(w.nl, w.scalars, w.p, w.Ap, w.x, w.r, w.partials2, &np[l], w.st));
+                }
             }
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_XR);
@@ -431,30 +516,32 @@ struct Engine {
             nvtxRangePushA("Dot_Product");
             if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch)) return 1;  // convergence, beta
             nvtxRangePop();
-            Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_RED_RR);
-            if (!multi) {
-                for (auto& w : ws.ranks) {  // K3: p = r + beta p
-                    B200_CUDA(cudaSetDevice(w.dev));
-                    B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
+            if (!dx) {
+                Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
+                if (!multi) {
+                    for (auto& w : ws.ranks) {  // K3: p = r + beta p
+                        B200_CUDA(cudaSetDevice(w.dev));
+                        B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
+                    }
+                } else {
+                    // K3 + halo push in one launch: the edge elements of the new p go straight into the
+                    // neighbours' landing buffers, the last CTA publishes the arrival epoch
+                    const uint32_t e = ++g.halo_epoch;
+                    for (auto& w : ws.ranks) {
+                        B200_CUDA(cudaSetDevice(w.dev));
+                        double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
+                        double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
+                        uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
+                        uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
+                        B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, ws.grid, dprev, dnext, fprev, fnext, e,
+                                                     g.xchg[w.rank], w.st));
+                    }
                 }
-            } else {
-                // K3 + halo push in one launch: the edge elements of the new p go straight into the
-                // neighbours' landing buffers, the last CTA publishes the arrival epoch
-                const uint32_t e = ++g.halo_epoch;
-                for (auto& w : ws.ranks) {
-                    B200_CUDA(cudaSetDevice(w.dev));
-                    double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
-                    double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
-                    uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
-                    uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
-                    B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, ws.grid, dprev, dnext, fprev, fnext, e,
-                                                 g.xchg[w.rank], w.st));
-                }
+                B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
+                pt.mark(T_P);
             }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_P);
             RankWs& w0 = ws.ranks[0];
             B200_CUDA(cudaSetDevice(w0.dev));
             B200_CUDA(cudaEventRecord(iter_event(w0, it), w0.st));
@@ -466,6 +553,16 @@ struct Engine {
                            (double)w0.status->residual, (double)w0.status->residual / (double)w0.status->b_norm);
                 if (w0.status->converged || w0.status->error) done = true;
             }
+        }
+        const size_t loop_mark1 = pt.used;
+        if (dx) {
+            // the x update of the last completed iteration is still pending: x += alpha p_last
+            for (auto& w : ws.ranks) {
+                B200_CUDA(cudaSetDevice(w.dev));
+                B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, w.st));
+            }
+            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
+            pt.mark(T_P);
         }
         (void)launched;
         for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaEventRecord(w.ev1, w.st)); }
@@ -492,7 +589,7 @@ struct Engine {
             for (size_t k = 1; k < pt.used; k++) {
                 // launches enqueued after convergence (the host polls kLag iterations behind) are
                 // no-ops on the device: keep them out of the per-phase times and launch counts
-                if (k >= loop_mark0 && (k - loop_mark0) / marks_per_iter >= (size_t)out->iterations) break;
+                if (k >= loop_mark0 && k < loop_mark1 && (k - loop_mark0) / marks_per_iter >= (size_t)out->iterations) continue;
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, w0.phase_ev[k - 1], w0.phase_ev[k]);
                 out->phase_ms[pt.tags[k]] += ms;

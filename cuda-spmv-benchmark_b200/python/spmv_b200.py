@@ -100,7 +100,8 @@ C_SYMBOLS = [
     "b200_stencil5_variant_info", "b200_csr_variant_info", "b200_csr_set_default_variant", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
-    "b200_cg_update_p_push",
+    "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_update_r_push", "b200_cg_halo_dir",
+    "b200_cg_finish_x", "b200_cg_set_schedule",
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
@@ -176,6 +177,13 @@ def load():
     L.b200_cg_update_p.argtypes = [ll, vp, vp, vp, vp]
     L.b200_cg_reduce.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp]
     L.b200_cg_update_p_push.argtypes = [ll, vp, vp, vp, i32, vp, vp, vp, vp, C.c_uint32, vp, vp]
+    L.b200_cg_spmv_fused.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.b200_cg_update_r.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), vp]
+    L.b200_cg_update_r_push.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), i32, vp, vp, vp, vp, C.c_uint32, vp, vp]
+    L.b200_cg_halo_dir.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, C.c_uint32, vp, i32, vp]
+    L.b200_cg_finish_x.argtypes = [ll, vp, vp, vp, vp, vp]
+    L.b200_cg_set_schedule.restype = None
+    L.b200_cg_set_schedule.argtypes = [i32]
     L.b200_dot_partials.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.b200_residual_init_generic.argtypes = [ll, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
     L.b200_checksum_partials.argtypes = [ll, vp, vp, vp, C.POINTER(i32), vp]

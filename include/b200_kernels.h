@@ -171,6 +171,36 @@ int b200_halo_push(const double* d_v_local, long long n_local, int halo, double*
 int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p, int halo,
                           double* d_dst_prev, double* d_dst_next, uint32_t* d_flag_prev,
                           uint32_t* d_flag_next, uint32_t epoch, void* d_my_xchg, b200_stream stream);
+
+/* ---- "deferred x" CG schedule: 4 launches and 112 B/row per iteration ----------------------
+ * Same recurrences as cg_solve_device (src/solvers/cg_solver.cu:538-638), regrouped:
+ *   b200_cg_spmv_fused : p_new = r + beta p_old (update_p_kernel :91-96), x += alpha_prev p_old
+ *                        (axpy_kernel_device :59-66, one iteration late), Ap = A p_new and the p.Ap
+ *                        partials, in ONE pass of the STENCIL5 kernel.  band halos hold the NEW p.
+ *   b200_cg_update_r   : r -= alpha Ap (axpy_sub_kernel_device :70-78) and the r.r partials, summed
+ *                        in the order of b200_cg_update_xr.  The _push form also stores the first /
+ *                        last `halo` elements of r into the neighbours' landing buffers.
+ *   b200_cg_halo_dir   : halo copies of p follow the same recurrence from the pushed r edges.
+ *   b200_cg_finish_x   : the x update still pending after the last iteration.
+ * Every iterate is bit-identical to the 5-launch schedule.                                      */
+int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
+                       double* d_x, double* d_Ap, double* d_partials, const void* d_scalars,
+                       b200_stream stream);
+int b200_cg_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
+                     double* d_partials, int* n_partials_out, b200_stream stream);
+int b200_cg_update_r_push(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
+                          double* d_partials, int* n_partials_out, int halo, double* d_dst_prev,
+                          double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next,
+                          uint32_t epoch, void* d_my_xchg, b200_stream stream);
+int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const double* d_pold_prev,
+                     const double* d_pold_next, double* d_pnew_prev, double* d_pnew_next, int halo,
+                     const uint32_t* d_flag_prev, const uint32_t* d_flag_next, uint32_t epoch,
+                     void* d_scalars, int beta_zero, b200_stream stream);
+int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
+                     double* d_x, b200_stream stream);
+/* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 5-launch schedule;
+ * the environment variable B200_CG_SCHEDULE=classic selects 0 at start-up */
+void b200_cg_set_schedule(int deferred_x);
 /* offsets of the halo flags inside an exchange area */
 size_t b200_xchg_flag_prev_offset(void);
 size_t b200_xchg_flag_next_offset(void);

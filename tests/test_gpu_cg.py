@@ -198,3 +198,58 @@ def test_halo_mgpu_operator(B, orc, torch_cuda):
         op.free()
     finally:
         del os.environ["B200_GPUS"]
+
+
+@pytest.mark.parametrize("n", [3, 64, 81, 130, 700])
+@pytest.mark.parametrize("max_iters", [1000, 1, 2, 5])
+def test_cg_deferred_x_schedule_bit_identical_to_classic(B, torch_cuda, n, max_iters):
+    """The 4-launch deferred-x schedule (p formed inside the SpMV, x retired one iteration late,
+    r.r summed in K2's order) must reproduce the classic 5-launch schedule bit for bit: iterates,
+    residual, iteration count -- also when the solve is cut off by max_iters (pending x update)."""
+    L = B.load()
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(n)
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    out = []
+    try:
+        for sched in (0, 1):
+            L.b200_cg_set_schedule(sched)
+            x, st, op = solve_device(B, b"stencil5-csr", hm, b, x0, max_iters=max_iters)
+            out.append((x, st))
+            op.contents.free()
+    finally:
+        L.b200_cg_set_schedule(1)
+    (xc, sc), (xd, sd) = out
+    assert sc["iterations"] == sd["iterations"] and sc["converged"] == sd["converged"]
+    assert sc["residual_norm"] == sd["residual_norm"]
+    assert np.array_equal(xc, xd)
+
+
+@pytest.mark.parametrize("n,P", [(81, 2), (64, 8), (130, 3), (512, 4)])
+def test_cg_mgpu_deferred_x_schedule_bit_identical_to_classic(B, torch_cuda, n, P):
+    """same, over P virtual ranks: r-edge push fused into K2r, halo copies of the direction kept by
+    cg_halo_dir (p_halo = r_halo + beta p_halo_old)"""
+    L = B.load()
+    N = n * n
+    devs = (C.c_int * P)(*([0] * P))
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(n + P)
+    b = rng.standard_normal(N)
+    out = []
+    try:
+        for sched in (0, 1):
+            L.b200_cg_set_schedule(sched)
+            assert L.b200_mgpu_init_single_process(P, devs, n) == 0
+            x = rng.standard_normal(N) if False else np.full(N, 0.25)
+            st = B.CGStatsMultiGPU()
+            rc = L.cg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(timers=1), C.byref(st))
+            assert rc == 0
+            out.append((x, st.iterations, st.residual_norm, st.converged))
+            L.b200_mgpu_finalize()
+    finally:
+        L.b200_cg_set_schedule(1)
+        L.b200_mgpu_finalize()
+    (xc, ic, rc_, cc), (xd, id_, rd, cd) = out
+    assert ic == id_ and cc == cd == 1 and rc_ == rd
+    assert np.array_equal(xc, xd)

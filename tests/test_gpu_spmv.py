@@ -73,7 +73,7 @@ def test_device_generation_band_slices(B, orc, torch_cuda, n, P):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 33, 34, 64, 65, 66, 67, 81, 130, 257, 600])
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 9, 12, 13])
 def test_stencil5_csr_bit_exact(B, orc, torch_cuda, n, variant):
     torch = torch_cuda
     L = B.load()

@@ -5,7 +5,7 @@
 
 Every kernel is timed with CUDA events on the launching stream after warm-up; working sets are
 far larger than the 126 MB L2.  Achieved GB/s uses ALGORITHMIC bytes:
-STENCIL5 8*nnz + 16*N, CSR 12*nnz + 4(N+1) + 16*N, ELLPACK 76*N, K2 48*N, K3 24*N.
+STENCIL5 8*nnz + 16*N (fused K1F: 8*nnz + 48*N), CSR 12*nnz + 4(N+1) + 16*N, ELLPACK 76*N, K2 48*N, K3 24*N.
 """
 import argparse
 import ctypes as C
@@ -90,6 +90,11 @@ def main():
     if "stencil" in what:
         st_bytes = 8.0 * nnz + 16.0 * N
         partials = torch.empty(1 << 22, dtype=torch.float64, device="cuda")
+        if "fused" in what:
+            fr, fp, fx = (torch.ones(N, dtype=torch.float64, device="cuda") for _ in range(3))
+            fsc = torch.zeros(64, dtype=torch.float64, device="cuda")
+            fsc[3] = 0.5   # alpha
+            fsc[4] = 0.25  # beta
         for v in [int(t) for t in a.variants.split(",")]:
             info = L.b200_stencil5_variant_info(v)
             if info is None:
@@ -103,6 +108,10 @@ def main():
                 ms, best = timeit(lambda: B.check(L.b200_cg_spmv_dot(C.byref(band), dptr(x), dptr(y), dptr(partials),
                                                                      None, s), "dot"))
                 rec("stencil5_dot", ms, best, st_bytes, variant=v, rows_per_item=R)
+                if "fused" in what:
+                    ms, best = timeit(lambda: B.check(L.b200_cg_spmv_fused(C.byref(band), dptr(x), dptr(fr), dptr(fp), dptr(fx),
+                                                                           dptr(y), dptr(partials), dptr(fsc), s), "fused"))
+                    rec("stencil5_fused(K1F)", ms, best, 8.0 * nnz + 48.0 * N, variant=v, rows_per_item=R)
         del partials
 
     if "cg" in what:
