@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=20000)
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling (BASELINE configs[4]): 20k x 20k rows PER GPU, square grid of side "
+                         "20000*sqrt(N) rounded to a multiple of 2N (bands stay grid-row aligned); not the headline metric")
     ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operators", action="store_true", help="skip the 10k x 10k operator comparison (configs[1])")
@@ -222,6 +225,13 @@ def run_b200(args):
             raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
     torch.cuda.set_device(local_rank)
     L = B.load()
+    if args.weak:
+        # the reference's weak-scaling recipe (scripts/benchmarking/benchmark_weak_scaling.sh:15-21: constant
+        # unknowns per GPU, square grids n0*sqrt(P)); MatrixData.rows is a 32-bit int in the reference's API,
+        # so the side is capped at 46340 (N < 2^31): 8 GPUs then hold 268M rows each instead of 400M
+        import math
+        step = 2 * world
+        args.grid = min(int(round(20000 * math.sqrt(world) / step)) * step, 46340 // step * step)
     n = args.grid
     N = n * n
     dist = None
@@ -346,12 +356,15 @@ def run_b200(args):
         iter_bytes = 128.0 * rows_local          # K1 56 + K2 48 + K3 24
         solve_bytes = (72.0 + 128.0 * iters) * rows_local
     line = {
-        "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC if not args.weak else "cg_solve_ms_weak_20k_x_20k_rows_per_gpu_stencil5_fp64",
+        "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "dtype": "f64",
         "data": "synthetic", "impl": "b200",
         "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (n, n), "grid": n, "rows": N,
                    "nnz": 5 * N - 4 * n, "tol": TOL, "iterations": iters, "operator": "stencil5-csr",
                    "partition": "row bands x%d" % world,
+                   "rows_per_gpu": nl,
                    "cache": "vectors (3.2 GB each) and matrix (16 GB values) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 16 * nl, "d2h_bytes_per_step": 8 * nl,
                 "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
@@ -375,7 +388,7 @@ def run_b200(args):
                                        [round(v, 4) for v in phase_sum])),
         "clocks": clocks,
     }
-    if world == 1 and not args.no_operators:
+    if world == 1 and not args.no_operators and not args.weak:
         op.contents.free()
         torch.cuda.empty_cache()
         line["operators_10k"] = operator_table(L, B, torch, peak)
