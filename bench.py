@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=20000)
+    ap.add_argument("--weak-cap32", action="store_true", help="with --weak: keep the row count below 2^31")
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling (BASELINE configs[4]): 20k x 20k rows PER GPU, square grid of side "
                          "20000*sqrt(N) rounded to a multiple of 2N (bands stay grid-row aligned); not the headline metric")
@@ -227,11 +228,14 @@ def run_b200(args):
     L = B.load()
     if args.weak:
         # the reference's weak-scaling recipe (scripts/benchmarking/benchmark_weak_scaling.sh:15-21: constant
-        # unknowns per GPU, square grids n0*sqrt(P)); MatrixData.rows is a 32-bit int in the reference's API,
-        # so the side is capped at 46340 (N < 2^31): 8 GPUs then hold 268M rows each instead of 400M
+        # unknowns per GPU, square grids n0*sqrt(P)).  8 GPUs = 56576^2 = 3.2e9 unknowns: beyond the 32-bit
+        # MatrixData.rows of the reference API; the synthetic-stencil path goes by grid_size (64-bit row ids,
+        # columns modulo 2^32, < 2^31 non-zeros per band).  --weak-cap32 keeps N below 2^31 instead.
         import math
         step = 2 * world
-        args.grid = min(int(round(20000 * math.sqrt(world) / step)) * step, 46340 // step * step)
+        args.grid = int(round(20000 * math.sqrt(world) / step)) * step
+        if args.weak_cap32:
+            args.grid = min(args.grid, 46340 // step * step)
     n = args.grid
     N = n * n
     dist = None

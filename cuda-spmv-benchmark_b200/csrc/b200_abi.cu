@@ -681,7 +681,10 @@ extern "C" int b200_gen_stencil5_csr(int grid_size, long long row_offset, long l
                                      double neighbour, int* d_row_ptr, int* d_col_idx, double* d_values,
                                      b200_stream stream) {
     if (!d_row_ptr || !d_col_idx || !d_values || grid_size < 1) return fail(B200_EINVAL, "gen csr: bad argument");
-    if ((long long)grid_size * grid_size > 2147483647LL) return fail(B200_EINVAL, "gen csr: 32-bit column ids overflow");
+    // CSR column ids are stored modulo 2^32 and read back as unsigned (csrc/stencil5.cuh): the grid may
+    // exceed 2^31 rows as long as it stays below 2^32 and the band below 2^31 non-zeros
+    if ((long long)grid_size * grid_size >= 4294967295LL) return fail(B200_EINVAL, "gen csr: column ids exceed 32 bits");
+    if (n_local < 0 || 5 * n_local >= 2147483647LL) return fail(B200_EINVAL, "gen csr: band exceeds 2^31 non-zeros");
     gen_stencil5_csr_kernel<<<gen_grid(n_local + 1), 256, 0, (cudaStream_t)stream>>>(grid_size, row_offset, n_local, center,
                                                                                     neighbour, d_row_ptr, d_col_idx, d_values);
     return check_launch("gen_stencil5_csr_kernel");

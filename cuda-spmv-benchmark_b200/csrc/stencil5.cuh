@@ -113,7 +113,9 @@ __device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long 
     else { s = lr * 5; e = s + 5; }  // ELLPACK width 5, padding index -1
     double sum = 0.0, xc = 0.0;
     for (long long k = s; k < e; k++) {
-        const long long c = a.col_idx[k];
+        // CSR column ids are read as unsigned: grids beyond 46340^2 rows (multi-GPU weak scaling) store
+        // global columns modulo 2^32; only the ELLPACK layout has padding (-1)
+        const long long c = a.row_ptr != nullptr ? (long long)(unsigned int)a.col_idx[k] : (long long)a.col_idx[k];
         if (c < 0) continue;
         const double xv = x_at<MODE, CG_LOADS>(a, c - a.row_offset, beta);
         if (c == r) xc = xv;

@@ -632,7 +632,7 @@ void partition(long long N, int P, int r, long long* nl, long long* off) {
 
 // (re)build the workspace for this matrix / world; returns 0 when ws is ready
 int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Engine* eng) {
-    const long long N = mat->rows;
+    const long long N = rows64(mat);
     // Workspace re-use between solves.  The vectors only depend on the shape; a band owned by the
     // workspace is only trusted again when its content is fully determined by the shape (synthetic
     // stencil) -- bands cut from caller-provided entries are rebuilt on every call, like the
@@ -774,7 +774,7 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
         if (b200_mgpu_init_single_process(world, devs, mat->grid_size > 0 ? mat->grid_size : 1)) return 1;
     }
     const long long n = mat->grid_size;
-    if (n < 1 || n * n != (long long)mat->rows) {
+    if (n < 1 || n * n != rows64(mat)) {
         fprintf(stderr, "[ERROR] cg_solve_mgpu_partitioned needs a stencil matrix with STENCIL_GRID_SIZE\n");
         return 1;
     }
@@ -782,10 +782,18 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
         fprintf(stderr, "[ERROR] grid %lld exceeds the halo capacity %zu of the active multi-GPU world\n", n, g.halo_cap);
         return 1;
     }
-    if (g.world > 1 && (long long)mat->rows / g.world < n) {
-        fprintf(stderr, "[ERROR] band of %lld rows is smaller than one grid row (%lld)\n",
-                (long long)mat->rows / g.world, n);
+    if (g.world > 1 && rows64(mat) / g.world < n) {
+        fprintf(stderr, "[ERROR] band of %lld rows is smaller than one grid row (%lld)\n", rows64(mat) / g.world, n);
         return 1;
+    }
+    {
+        // a band is addressed with 32-bit local offsets: fewer than 2^31 non-zeros per rank; global
+        // column ids are stored modulo 2^32
+        const long long band_rows = rows64(mat) / g.world + rows64(mat) % g.world;
+        if (5 * band_rows >= 2147483647LL || rows64(mat) >= 4294967295LL) {
+            fprintf(stderr, "[ERROR] %lld rows over %d rank(s): a band must stay below 2^31 non-zeros\n", rows64(mat), g.world);
+            return 1;
+        }
     }
     Engine eng;
     eng.op = nullptr;

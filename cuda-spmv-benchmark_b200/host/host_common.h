@@ -40,6 +40,12 @@ namespace b200host {
 
 // Is `mat` the synthetic stencil of the B200 extension (entries == NULL, grid_size > 0)?
 inline bool is_synthetic(const MatrixData* m) { return m && m->entries == nullptr && m->grid_size > 0; }
+// Row count as a 64-bit number.  MatrixData.rows is a 32-bit int (reference include/io.h:50-56); the
+// synthetic stencil is defined by its grid size alone, so it may exceed 2^31 rows (multi-GPU only:
+// a band still holds fewer than 2^31 non-zeros) -- rows / cols / nnz are then saturated and ignored.
+inline long long rows64(const MatrixData* m) {
+    return is_synthetic(m) ? (long long)m->grid_size * m->grid_size : (long long)m->rows;
+}
 
 // Device-resident matrix slice of one operator (or one band of the multi-GPU solver).
 struct DeviceBand {

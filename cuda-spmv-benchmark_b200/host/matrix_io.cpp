@@ -402,6 +402,9 @@ extern "C" int ensure_ellpack_structure_built(MatrixData* mat) {
 extern "C" MatrixData b200_synthetic_stencil(int n) {
     MatrixData m;
     const long long N = (long long)n * n, nnz = 5LL * n * n - 4LL * n;
-    m.rows = (int)N; m.cols = (int)N; m.nnz = (int)nnz; m.grid_size = n; m.entries = nullptr;
+    // the 32-bit fields saturate beyond their range (grids above 46340 / 20724): rows64() and the device
+    // generators go by grid_size
+    const long long cap = 2147483647LL;
+    m.rows = (int)(N < cap ? N : cap); m.cols = m.rows; m.nnz = (int)(nnz < cap ? nnz : cap); m.grid_size = n; m.entries = nullptr;
     return m;
 }

@@ -146,6 +146,55 @@ def test_stencil5_halo_bands_bit_exact(B, orc, torch_cuda, n, P):
         assert np.array_equal(y.cpu().numpy(), y_full[off:off + nl]), (n, P, g)
 
 
+@pytest.mark.parametrize("where", ["last", "cross_2_31", "cross_2_32_minus"])
+def test_stencil5_band_beyond_2_31_rows(B, torch_cuda, where):
+    """Weak scaling at 8 x 400M rows puts bands beyond row 2^31 (the reference's int ids overflow
+    there): 64-bit row offsets, global column ids stored modulo 2^32 and read back as unsigned by
+    the boundary rows.  A thin band of a 56576^2 grid (3.2e9 rows) is generated on the device and
+    multiplied with halos; the expected product comes from the stencil formula in numpy."""
+    torch = torch_cuda
+    L = B.load()
+    n = 56576
+    N = n * n
+    rows_band = 3 * n + 1234  # not grid-row aligned on purpose
+    off = {"last": N - rows_band, "cross_2_31": (2 ** 31 // n) * n - n - 17, "cross_2_32_minus": N - 2 * rows_band - 5}[where]
+    nl = rows_band
+    rp, ci, va, lnnz = device_stencil_csr(B, torch, n, off, nl)
+    rng = np.random.default_rng(5)
+    xl_h, hp_h, hn_h = rng.standard_normal(nl), rng.standard_normal(n), rng.standard_normal(n)
+    last = off + nl == N
+    xl, hp = torch.from_numpy(xl_h).cuda(), torch.from_numpy(hp_h).cuda()
+    hn = None if last else torch.from_numpy(hn_h).cuda()
+    y = torch.full((nl,), float("nan"), dtype=torch.float64, device="cuda")
+    band = B.Band(rp.data_ptr(), ci.data_ptr(), va.data_ptr(), lnnz + 2, off, nl, n, 0, hp.data_ptr(),
+                  hn.data_ptr() if hn is not None else None, None, None, 0, 0, 0)
+    B.check(L.b200_stencil5_spmv(C.byref(band), dptr(xl), dptr(y), None), "band spmv")
+    torch.cuda.synchronize()
+    # expected: x extended by the halos, y = 5 x[r] - x[r-1] - x[r+1] - x[r-n] - x[r+n] inside the grid,
+    # accumulated in the reference order (W, C, E, N, S for interior rows; k order N,W,C,E,S at the boundary)
+    ext = np.concatenate([hp_h, xl_h, hn_h if not last else np.zeros(n)])
+    r = off + np.arange(nl, dtype=np.int64)
+    i, j = r // n, r % n
+    c = ext[n:n + nl]
+    W = np.where(j > 0, ext[n - 1:n - 1 + nl], 0.0)
+    E = np.where(j < n - 1, ext[n + 1:n + 1 + nl], 0.0)
+    Nn = np.where(i > 0, ext[0:nl], 0.0)
+    S = np.where(i < n - 1, ext[2 * n:2 * n + nl], 0.0)
+    interior = (i > 0) & (i < n - 1) & (j > 0) & (j < n - 1)
+    # every product with -1 is exact, so only the order of the additions matters (no fma difference)
+    y_int = ((((5.0 * c) - W) - E) - Nn) - S
+    y_bnd = np.zeros(nl)
+    for cond, v in ((i > 0, Nn), (j > 0, W)):
+        y_bnd = np.where(cond, y_bnd - v, y_bnd)
+    y_bnd = y_bnd + 5.0 * c
+    for cond, v in ((j < n - 1, E), (i < n - 1, S)):
+        y_bnd = np.where(cond, y_bnd - v, y_bnd)
+    yo = np.where(interior, y_int, y_bnd)
+    yd = y.cpu().numpy()
+    assert np.abs(yd - yo).max() <= 4e-15 * np.abs(yo).max()
+    assert np.array_equal(yd[interior], yo[interior])
+
+
 def random_csr(rng, rows, cols, lens):
     ent = []
     for r, ln in enumerate(lens):

@@ -160,3 +160,26 @@ def test_cg_json_export_schema(B, tmp_path):
     L.export_cg_csv(p3.encode(), b"stencil5-csr", hs.ptr(), C.byref(bs), C.byref(cs), True)
     lines = open(p3).read().splitlines()
     assert lines[0].startswith("mode,rows,cols,nnz,grid_size,converged,iterations") and lines[1].startswith("stencil5-csr,16,16,64,4,1,14,")
+
+
+def test_mpirun_shim_maps_ranks_to_gpus():
+    """reference scripts call `mpirun -np P ./bin/cg_solver_mgpu_stencil <mtx> --json=F`
+    (scripts/benchmarking/benchmark_weak_scaling.sh, benchmark_problem_sizes.sh): the shim must turn
+    that into one process with --gpus=P and drop the MPI-only options"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "cuda-spmv-benchmark_b200", "scripts", "mpirun")
+    env = dict(os.environ, B200_MPIRUN_DRYRUN="1")
+
+    def run(*args):
+        return subprocess.run([shim, *args], env=env, capture_output=True, text=True)
+    r = run("-np", "8", "--allow-run-as-root", "--bind-to", "none", "--mca", "btl", "self,vader",
+            "./bin/cg_solver_mgpu_stencil", "matrix/20000", "--json=out.json", "--timers")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "./bin/cg_solver_mgpu_stencil matrix/20000 --json=out.json --timers --gpus=8"
+    r = run("-n", "2", "./bin/cg_solver_mgpu_stencil", "m.mtx")
+    assert r.stdout.strip() == "./bin/cg_solver_mgpu_stencil m.mtx --gpus=2"
+    r = run("-np", "1", "./bin/cg_solver", "m.mtx", "--mode=stencil5-csr")
+    assert r.stdout.strip() == "./bin/cg_solver m.mtx --mode=stencil5-csr"
+    assert run("-np", "4").returncode == 2
