@@ -597,9 +597,10 @@ extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double
     return check_launch("cg_finish_x_kernel");
 }
 
-extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
-                              void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
-                              uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream) {
+namespace {
+int launch_reduce(const double* d_partials, int n_partials, int which, int phases, double tol, void* d_scalars,
+                  void* h_status_mapped, double* d_out, int rank, int world, uint32_t epoch, void* const* d_peer_xchg,
+                  double* d_stash, const HaloDirArgs* hd, cudaStream_t stream) {
     if (!d_partials || n_partials < 0) return fail(B200_EINVAL, "cg_reduce: bad partials");
     if (which != RED_SUM && !d_scalars) return fail(B200_EINVAL, "cg_reduce: NULL scalars");
     if (which == RED_SUM && !d_out) return fail(B200_EINVAL, "cg_reduce: NULL out");
@@ -616,8 +617,35 @@ extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int whic
         for (int r = 0; r < world; r++) a.peer_xchg[r] = static_cast<XchgArea*>(d_peer_xchg[r]);
         a.my_xchg = a.peer_xchg[rank];
     }
-    cg_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    if (hd) { a.with_halo_dir = 1; a.hd = *hd; }
+    cg_reduce_kernel<<<1, 1024, 0, stream>>>(a);
     return check_launch("cg_reduce_kernel");
+}
+}  // namespace
+
+extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
+                              void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
+                              uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream) {
+    return launch_reduce(d_partials, n_partials, which, phases, tol, d_scalars, h_status_mapped, d_out, rank, world, epoch,
+                         d_peer_xchg, d_stash, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b200_cg_reduce_rr_dir(const double* d_partials, int n_partials, int phases, double tol, void* d_scalars,
+                                     void* h_status_mapped, int rank, int world, uint32_t epoch,
+                                     void* const* d_peer_xchg, double* d_stash, const double* d_r_prev,
+                                     const double* d_r_next, const double* d_pold_prev, const double* d_pold_next,
+                                     double* d_pnew_prev, double* d_pnew_next, int halo, const uint32_t* d_flag_prev,
+                                     const uint32_t* d_flag_next, uint32_t halo_epoch, b200_stream stream) {
+    if (halo < 1) return fail(B200_EINVAL, "cg_reduce_rr_dir: bad halo");
+    if ((d_r_prev && (!d_pnew_prev || !d_flag_prev || !d_pold_prev)) || (d_r_next && (!d_pnew_next || !d_flag_next || !d_pold_next)))
+        return fail(B200_EINVAL, "cg_reduce_rr_dir: NULL buffer");
+    HaloDirArgs h;
+    h.r_prev = d_r_prev; h.r_next = d_r_next; h.pold_prev = d_pold_prev; h.pold_next = d_pold_next;
+    h.pnew_prev = d_pnew_prev; h.pnew_next = d_pnew_next; h.halo = halo;
+    h.flag_prev = d_flag_prev; h.flag_next = d_flag_next; h.epoch = halo_epoch;
+    h.sc = static_cast<CGScalars*>(d_scalars); h.beta_zero = 0;
+    return launch_reduce(d_partials, n_partials, RED_RR, phases, tol, d_scalars, h_status_mapped, nullptr, rank, world,
+                         epoch, d_peer_xchg, d_stash, (d_r_prev || d_r_next) ? &h : nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b200_dot_partials(long long n, const void* d_scalars, const double* d_x, const double* d_y,

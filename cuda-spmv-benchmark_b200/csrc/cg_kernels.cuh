@@ -64,6 +64,22 @@ struct HaloPushArgs {
     const CGScalars* sc;
 };
 
+// halo copies of the search direction (deferred-x schedule): see cg_halo_dir_kernel
+struct HaloDirArgs {
+    const double* r_prev;  // landing buffers written by the neighbours (NULL at the ends)
+    const double* r_next;
+    const double* pold_prev;
+    const double* pold_next;
+    double* pnew_prev;
+    double* pnew_next;
+    int halo;
+    const uint32_t* flag_prev;
+    const uint32_t* flag_next;
+    uint32_t epoch;
+    CGScalars* sc;
+    int beta_zero;
+};
+
 enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3 };
 enum { RED_PUSH = 1, RED_COMBINE = 2 };
 
@@ -82,6 +98,10 @@ struct ReduceArgs {
     XchgArea* my_xchg;
     XchgArea* peer_xchg[B200_MAX_RANKS];
     double* stash;  // local: my partial sum between PUSH and COMBINE launches
+    // RED_RR, multi-GPU deferred-x schedule: once beta is known the same CTA advances the halo copies
+    // of the direction, p_halo = fma(beta, p_halo_old, r_halo) (one launch less per iteration)
+    int with_halo_dir;
+    HaloDirArgs hd;
 };
 
 // One CTA of 1024 threads.  Fixed-order final sum of the per-CTA partials, optional rank
@@ -140,37 +160,63 @@ __global__ void __launch_bounds__(1024) cg_reduce_kernel(const ReduceArgs a) {
             for (int r = 0; r < a.world; r++) total += rank_sum[r];  // rank order: same on every GPU
         }
     }
-    if (t != 0) return;
-
-    if (a.which == RED_SUM) {
-        *a.out = total;
-    } else if (a.which == RED_RR0) {
-        sc->rr_old = total;
-        sc->b_norm = sqrt(total);
-        sc->residual = sc->b_norm;
-        if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
-    } else if (a.which == RED_PAP) {
-        sc->pAp = total;
-        sc->alpha = sc->rr_old / total;
-    } else {  // RED_RR
-        sc->rr_new = total;
-        const double res = sqrt(total);
-        sc->residual = res;
-        const int it = sc->iterations + 1;
-        sc->iterations = it;
-        const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
-        if (conv) {
-            sc->converged = 1;
-        } else {
-            sc->beta = total / sc->rr_old;
+    __shared__ int s_go_halo;
+    if (t == 0) {
+        s_go_halo = 0;
+        if (a.which == RED_SUM) {
+            *a.out = total;
+        } else if (a.which == RED_RR0) {
             sc->rr_old = total;
+            sc->b_norm = sqrt(total);
+            sc->residual = sc->b_norm;
+            if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
+        } else if (a.which == RED_PAP) {
+            sc->pAp = total;
+            sc->alpha = sc->rr_old / total;
+        } else {  // RED_RR
+            sc->rr_new = total;
+            const double res = sqrt(total);
+            sc->residual = res;
+            const int it = sc->iterations + 1;
+            sc->iterations = it;
+            const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
+            if (conv) {
+                sc->converged = 1;
+            } else {
+                sc->beta = total / sc->rr_old;
+                sc->rr_old = total;
+                s_go_halo = a.with_halo_dir;
+            }
+            if (a.status) {
+                // the host reads these only after synchronising on an event recorded behind this
+                // kernel (cg_engine.cpp), so no system-scope fence is needed here
+                a.status->residual = res;
+                a.status->iterations = it;
+                a.status->converged = conv;
+            }
         }
-        if (a.status) {
-            a.status->residual = res;
-            a.status->iterations = it;
-            a.status->converged = conv;
-            __threadfence_system();
+    }
+    if (!a.with_halo_dir) return;
+    __syncthreads();
+    if (!s_go_halo) return;
+    // ---- halo copies of the new direction (the neighbours' r edges arrived before their LL words)
+    const HaloDirArgs& h = a.hd;
+    if (t == 0) {
+        const uint64_t t0 = globaltimer_ns();
+        const uint32_t* fl[2] = {h.r_prev ? h.flag_prev : nullptr, h.r_next ? h.flag_next : nullptr};
+        for (int d = 0; d < 2; d++) {
+            if (!fl[d]) continue;
+            while ((int32_t)(ld_acquire_sys(fl[d]) - h.epoch) < 0) {
+                if (sc->error || globaltimer_ns() - t0 > 8000000000ull) { sc->error = 1; break; }
+                __nanosleep(64);
+            }
         }
+    }
+    __syncthreads();
+    const double beta = sc->beta;
+    for (int i = t; i < h.halo; i += 1024) {
+        if (h.r_prev) h.pnew_prev[i] = fma(beta, h.pold_prev[i], __ldcg(h.r_prev + i));
+        if (h.r_next) h.pnew_next[i] = fma(beta, h.pold_next[i], __ldcg(h.r_next + i));
     }
 }
 
@@ -330,20 +376,6 @@ __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGS
 // of their NEW r; the halo copies of p follow the same recurrence as the local part,
 // p_halo = fma(beta, p_halo_old, r_halo), kept in two local ping-pong buffers.  beta_zero: first
 // direction (p0 = r0).  One small CTA group; waits (bounded) for the arrival epochs first.
-struct HaloDirArgs {
-    const double* r_prev;  // landing buffers written by the neighbours (NULL at the ends)
-    const double* r_next;
-    const double* pold_prev;
-    const double* pold_next;
-    double* pnew_prev;
-    double* pnew_next;
-    int halo;
-    const uint32_t* flag_prev;
-    const uint32_t* flag_next;
-    uint32_t epoch;
-    CGScalars* sc;
-    int beta_zero;
-};
 
 __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
     if (a.sc->converged) return;

@@ -330,7 +330,9 @@ struct Engine {
     SpmvOperator* op;     // generic path
     int n_partials_spmv[kMaxRanks];
 
-    int for_ranks_reduce(int which, double tol, const int* n_partials, bool second_buf, uint32_t epoch) {
+    // dir_it >= 0 (multi-GPU deferred-x schedule, which == 2): the reduce CTA also advances the halo
+    // copies of the direction from parity dir_it to dir_it + 1
+    int for_ranks_reduce(int which, double tol, const int* n_partials, bool second_buf, uint32_t epoch, int dir_it = -1) {
         const int phases_list_fused[1] = {3};
         const int phases_list_split[2] = {1, 2};
         const bool split = (g.world > 1 && g.single_device && ws.ranks.size() > 1);
@@ -340,6 +342,16 @@ struct Engine {
             for (size_t l = 0; l < ws.ranks.size(); l++) {
                 RankWs& w = ws.ranks[l];
                 B200_CUDA(cudaSetDevice(w.dev));
+                if (dir_it >= 0 && which == 2 && g.world > 1) {
+                    B200_K(b200_cg_reduce_rr_dir(second_buf ? w.partials2 : w.partials, n_partials[l], pl[pi], tol, w.scalars,
+                                                 w.status_dev, w.rank, g.world, epoch, g.xchg, w.stash,
+                                                 w.rank > 0 ? landing_prev(w.rank) : nullptr,
+                                                 w.rank < g.world - 1 ? landing_next(w.rank) : nullptr,
+                                                 halo_dir(w.rank, dir_it, 0), halo_dir(w.rank, dir_it, 1),
+                                                 halo_dir(w.rank, dir_it + 1, 0), halo_dir(w.rank, dir_it + 1, 1), ws.grid,
+                                                 flag_prev(w.rank), flag_next(w.rank), g.halo_epoch, w.st));
+                    continue;
+                }
                 B200_K(b200_cg_reduce(second_buf ? w.partials2 : w.partials, n_partials[l], which, pl[pi], tol,
                                       w.scalars, which == 3 ? nullptr : w.status_dev, w.sums, w.rank, g.world, epoch,
                                       g.world > 1 ? g.xchg : nullptr, w.stash, w.st));
@@ -431,28 +443,13 @@ struct Engine {
             pt.mark(T_HALO);
         }
         const size_t loop_mark0 = pt.used;            // first phase mark of the iteration loop
-        // classic: K1, R, K2, R, K3 (halo push fused into K3); deferred x: [H,] K1F, R, K2r, R
-        const size_t marks_per_iter = dx ? (multi ? 5 : 4) : 5;
+        // classic: K1, R, K2, R, K3 (halo push fused into K3); deferred x: K1F, R, K2r, R (+ halo direction)
+        const size_t marks_per_iter = dx ? 4 : 5;
         int launched = 0;
         bool done = false;
         Nvtx range_solver("CG_Solver");
         for (int it = 0; it < max_iters && !done; it++) {
             Nvtx range_iter("CG_Iteration");
-            if (dx && multi) {
-                // halo copies of the new direction (it >= 1): p_halo = r_halo + beta p_halo_old
-                Nvtx range_h("Halo_Direction");
-                for (auto& w : ws.ranks) {
-                    B200_CUDA(cudaSetDevice(w.dev));
-                    if (it >= 1)
-                        B200_K(b200_cg_halo_dir(w.rank > 0 ? landing_prev(w.rank) : nullptr,
-                                                w.rank < g.world - 1 ? landing_next(w.rank) : nullptr,
-                                                halo_dir(w.rank, it - 1, 0), halo_dir(w.rank, it - 1, 1),
-                                                halo_dir(w.rank, it, 0), halo_dir(w.rank, it, 1), ws.grid,
-                                                flag_prev(w.rank), flag_next(w.rank), g.halo_epoch, w.scalars, 0, w.st));
-                }
-                B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-                pt.mark(T_HALO);
-            }
             nvtxRangePushA("SpMV");
             for (size_t l = 0; l < L; l++) {  // K1: Ap = A p, partials p.Ap
                 RankWs& w = ws.ranks[l];
@@ -514,7 +511,9 @@ struct Engine {
             pt.mark(T_XR);
             nvtxRangePop();
             nvtxRangePushA("Dot_Product");
-            if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch)) return 1;  // convergence, beta
+            // convergence, beta; multi-GPU deferred-x: + halo copies of the next direction,
+            // p_halo = r_halo + beta p_halo_old (the r edges were pushed by K2r above)
+            if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch, (dx && multi) ? it : -1)) return 1;
             nvtxRangePop();
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_RED_RR);

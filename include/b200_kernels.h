@@ -196,6 +196,14 @@ int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const doubl
                      const double* d_pold_next, double* d_pnew_prev, double* d_pnew_next, int halo,
                      const uint32_t* d_flag_prev, const uint32_t* d_flag_next, uint32_t epoch,
                      void* d_scalars, int beta_zero, b200_stream stream);
+/* b200_cg_reduce(which = 2) and b200_cg_halo_dir in one launch: once beta is known the reduce CTA
+ * advances the halo copies of the direction (multi-GPU, deferred-x schedule) */
+int b200_cg_reduce_rr_dir(const double* d_partials, int n_partials, int phases, double tol, void* d_scalars,
+                          void* h_status_mapped, int rank, int world, uint32_t epoch,
+                          void* const* d_peer_xchg, double* d_stash, const double* d_r_prev,
+                          const double* d_r_next, const double* d_pold_prev, const double* d_pold_next,
+                          double* d_pnew_prev, double* d_pnew_next, int halo, const uint32_t* d_flag_prev,
+                          const uint32_t* d_flag_next, uint32_t halo_epoch, b200_stream stream);
 int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
                      double* d_x, b200_stream stream);
 /* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 5-launch schedule;
