@@ -255,12 +255,13 @@ const CsrVariant kCsrVariants[] = {
 const int kNumCsrVariants = (int)(sizeof(kCsrVariants) / sizeof(kCsrVariants[0]));
 
 std::atomic<int> g_csr_default_variant{0};
+thread_local long long g_csr_last_items = 0;  // items (= dot partials) of the last ring launch on this thread
 int csr_default_variant() { return g_csr_default_variant.load(std::memory_order_relaxed); }
 constexpr int kCsrGroupsPerItem = 32;  // 1024 rows per warp item
 
-template <int WARPS, int STAGES, int WIN, int MODE, int MINB>
+template <int WARPS, int STAGES, int WIN, int MODE, int MINB, bool DOT = false>
 int launch_csr_ring_mode(const CsrArgs& a, int gpw_override, cudaStream_t s) {
-    auto k = csr_ring_kernel<WARPS, STAGES, WIN, MODE, MINB>;
+    auto k = csr_ring_kernel<WARPS, STAGES, WIN, MODE, MINB, DOT>;
     const size_t smem = (size_t)WARPS * csr_ring_warp_bytes<STAGES, WIN>();
     static int resident_ctas = 0;  // per instantiation: CTAs that fit the whole GPU at once
     if (resident_ctas == 0) {
@@ -291,6 +292,8 @@ int launch_csr_ring_mode(const CsrArgs& a, int gpw_override, cudaStream_t s) {
     const long long warps = (groups + gpw - 1) / gpw;
     const long long blocks = (warps + WARPS - 1) / WARPS;
     if (blocks > 2147483647LL) return fail(B200_EINVAL, "csr: too many row blocks");
+    g_csr_last_items = warps;  // one dot partial per item
+    if (a.dot_partials && warps > a.dot_capacity) return fail(B200_EINVAL, "csr: dot partials buffer too small");
     k<<<(unsigned)blocks, WARPS * 32, smem, s>>>(a, (int)gpw);
     return check_launch("csr_ring_kernel");
 }
@@ -333,8 +336,16 @@ int launch_csr(const CsrArgs& a, int variant, cudaStream_t s) {
     variant %= 1000;
     // the bulk copies need 16-byte aligned arrays; anything else takes the register-staged kernel
     const bool aligned = (((uintptr_t)a.col_idx | (uintptr_t)a.values) & 15) == 0;
-    if (variant == 100 || !aligned) return launch_csr_legacy(a, s);
+    if (variant == 100 || !aligned) {
+        if (a.dot_partials) return fail(B200_EINVAL, "csr: the fused dot needs 16-byte aligned col_idx / values");
+        return launch_csr_legacy(a, s);
+    }
     if (variant >= kNumCsrVariants) variant = 0;
+    if (a.dot_partials) {  // fused x.y partials: compiled for the default variant only
+        if (a.row_ptr) return launch_csr_ring_mode<8, 4, 128, 0, 4, true>(a, gpw, s);
+        return csr_ring_ell_is_lpr<4, 128>(a.ell_width) ? launch_csr_ring_mode<8, 4, 128, 1, 4, true>(a, gpw, s)
+                                                        : launch_csr_ring_mode<8, 4, 128, 2, 4, true>(a, gpw, s);
+    }
     return a.row_ptr ? launch_csr_variant<false>(variant, gpw, a, s) : launch_csr_variant<true>(variant, gpw, a, s);
 }
 }  // namespace
@@ -390,10 +401,50 @@ extern "C" int b200_spmv_csr(const b200_csr_plan* plan, const int* d_row_ptr, co
                              double beta, b200_stream stream) {
     if (!plan || !d_row_ptr || !d_x || !d_y) return fail(B200_EINVAL, "csr: NULL argument");
     CsrArgs a;
+    memset(&a, 0, sizeof a);
     a.row_ptr = d_row_ptr; a.col_idx = d_col_idx; a.values = d_values; a.x = d_x; a.y = d_y;
     a.n_rows = n_rows; a.ell_width = 0; a.vector_threshold = plan->vector_threshold > 0 ? plan->vector_threshold : 32;
     a.alpha = alpha; a.beta = beta;
     return launch_csr(a, plan->variant, (cudaStream_t)stream);
+}
+
+extern "C" long long b200_csr_dot_partials_capacity(long long n_rows) {
+    // upper bound of the item count for any tuning variant: one item per 32-row group
+    return n_rows > 0 ? (n_rows + 31) / 32 : 0;
+}
+
+extern "C" int b200_spmv_csr_dot(const b200_csr_plan* plan, const int* d_row_ptr, const int* d_col_idx,
+                                 const double* d_values, const double* d_x, double* d_y, long long n_rows,
+                                 double* d_partials, long long partials_capacity, int* n_partials_out,
+                                 const void* d_scalars, b200_stream stream) {
+    if (!plan || !d_row_ptr || !d_x || !d_y || !d_partials) return fail(B200_EINVAL, "csr_dot: NULL argument");
+    CsrArgs a;
+    memset(&a, 0, sizeof a);
+    a.row_ptr = d_row_ptr; a.col_idx = d_col_idx; a.values = d_values; a.x = d_x; a.y = d_y;
+    a.n_rows = n_rows; a.ell_width = 0; a.vector_threshold = plan->vector_threshold > 0 ? plan->vector_threshold : 32;
+    a.alpha = 1.0; a.beta = 0.0;
+    a.dot_partials = d_partials; a.dot_capacity = partials_capacity;
+    if (d_scalars) a.converged = &static_cast<const CGScalars*>(d_scalars)->converged;
+    int rc = launch_csr(a, plan->variant, (cudaStream_t)stream);
+    if (rc == B200_OK && n_partials_out) *n_partials_out = (int)g_csr_last_items;
+    return rc;
+}
+
+extern "C" int b200_spmv_ellpack_dot(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
+                                     long long n_rows, int width, double* d_partials, long long partials_capacity,
+                                     int* n_partials_out, const void* d_scalars, b200_stream stream) {
+    if (!d_indices || !d_values || !d_x || !d_y || !d_partials) return fail(B200_EINVAL, "ellpack_dot: NULL argument");
+    if (width < 1 || width > 1000) return fail(B200_EINVAL, "ellpack: width outside [1, MAX_WIDTH]");
+    CsrArgs a;
+    memset(&a, 0, sizeof a);
+    a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
+    a.n_rows = n_rows; a.ell_width = width; a.vector_threshold = 1 << 20;
+    a.alpha = 1.0; a.beta = 0.0;
+    a.dot_partials = d_partials; a.dot_capacity = partials_capacity;
+    if (d_scalars) a.converged = &static_cast<const CGScalars*>(d_scalars)->converged;
+    int rc = launch_csr(a, 0, (cudaStream_t)stream);
+    if (rc == B200_OK && n_partials_out) *n_partials_out = (int)g_csr_last_items;
+    return rc;
 }
 
 extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
@@ -401,6 +452,7 @@ extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, c
     if (!d_indices || !d_values || !d_x || !d_y) return fail(B200_EINVAL, "ellpack: NULL argument");
     if (width < 1 || width > 1000) return fail(B200_EINVAL, "ellpack: width outside [1, MAX_WIDTH]");
     CsrArgs a;
+    memset(&a, 0, sizeof a);
     a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
     a.n_rows = n_rows; a.ell_width = width; a.vector_threshold = 1 << 20;  // ELLPACK rows are uniform: always stream
     a.alpha = alpha; a.beta = beta;

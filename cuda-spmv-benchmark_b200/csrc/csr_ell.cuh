@@ -32,6 +32,11 @@ struct CsrArgs {
     int vector_threshold;  // ring kernel: longest row of a 32-row group above which it goes warp-per-row
                            // (warp-stream kernel: mean entries per row of the group)
     double alpha, beta;
+    // optional fusion for CG (ring kernel only): partials[item] = sum over the item's rows of x[row] * y[row]
+    // (the p.Ap dot product of a square operator); `converged` (optional) turns the launch into a no-op
+    double* dot_partials;
+    long long dot_capacity;  // slots behind dot_partials (checked by the launcher)
+    const int* converged;
 };
 
 // histogram of row lengths: bin b counts rows with length in (2^(b-1), 2^b], bin 0 = empty/1
@@ -156,7 +161,8 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 //     difference to the sequential order, documented tolerance 1e-12).  Rows may be longer than
 //     the ring: they stream through it window by window.
 // Only __syncwarp is used; warps are fully independent.  col_idx and values must be 16-byte aligned
-// (the launcher routes anything else to csr_warp_stream_kernel above).
+// (the launcher routes anything else to csr_warp_stream_kernel above).  DOT = true additionally
+// writes one partial of x.y per item (CG: p.Ap), see CsrArgs::dot_partials.
 // ================================================================================================
 constexpr int kCsrPrefetch = 8;  // x values per row gathered one group ahead
 constexpr int kCsrExtentSlots = 4;  // row extents of 3 groups in flight (cp.async) + 1 being read
@@ -249,7 +255,7 @@ struct CsrGroup {
 // MODE: 0 = CSR (every group picks lane-per-row or warp-per-row), 1 = ELLPACK narrow enough for
 // lane-per-row throughout, 2 = wide ELLPACK, warp-per-row throughout (the host picks with
 // csr_ring_ell_is_lpr).
-template <int WARPS, int STAGES, int WIN, int MODE, int MINB>
+template <int WARPS, int STAGES, int WIN, int MODE, int MINB, bool DOT = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArgs a, const int groups_per_warp) {
     constexpr bool ELL = MODE != 0;
     constexpr int RING = STAGES * WIN, M = RING - 1, J = kCsrPrefetch;
@@ -259,6 +265,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(B200_FULL, threadIdx.x >> 5, 0);  // tells the compiler it is warp-uniform
+    if (a.converged != nullptr && *a.converged != 0) return;
 
     const long long Ra = ((long long)blockIdx.x * WARPS + warp) * groups_per_warp * 32;
     if (Ra >= a.n_rows) return;
@@ -456,6 +463,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
     CsrGroup cur, nxt;
     double* yp = a.y + Ra + lane;
     const double alpha = a.alpha, beta = a.beta;
+    constexpr bool dot = DOT;  // compiled separately: the plain SpMV pays nothing for the fusion
+    const double* xrow = xp + Ra + lane;  // dot fusion: x at the lane's own row
+    double dacc = 0.0;
     cur.lpr = true; cur.full = false; cur.s = cur.len = cur.gs = cur.nnz = cur.maxlen = 0;
     nxt = cur;
     fetch_extents(0);
@@ -468,10 +478,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
             else if (MODE == 2) sum = process_vec(cur, min(32, nrows - gi * 32));
             else sum = cur.lpr ? process_lpr(cur, xq) : process_vec(cur, min(32, nrows - gi * 32));
             if (gi * 32 + lane < nrows) {
-                if (beta == 0.0) __stcs(yp, alpha * sum);
-                else __stcs(yp, fma(alpha, sum, beta * *yp));
+                const double yv = (beta == 0.0) ? alpha * sum : fma(alpha, sum, beta * *yp);
+                __stcs(yp, yv);
+                if (dot) dacc = fma(__ldg(xrow), yv, dacc);
             }
             yp += 32;
+            xrow += 32;
         }
         if (gi >= -1) {
             release(nxt.gs);
@@ -483,6 +495,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
         cur = nxt;
         make_group(gi + 2, nxt);
         fetch_extents(gi + 5);
+    }
+    if (dot) {  // fixed order: lanes (butterfly) -> one slot per item -> final pass in item order
+        dacc = warp_sum(dacc);
+        if (lane == 0) a.dot_partials[(long long)blockIdx.x * WARPS + warp] = dacc;
     }
 }
 

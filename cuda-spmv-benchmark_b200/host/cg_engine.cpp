@@ -468,7 +468,8 @@ struct Engine {
                     wire_band(w, &band, true, g.halo_epoch);
                     B200_K(b200_cg_spmv_dot(&band, w.p, w.Ap, w.partials, w.scalars, w.st));
                     np[l] = n_partials_spmv[l];
-                } else {
+                } else if (operator_spmv_dot(op, w.p, w.Ap, w.partials, w.max_partials, &np[l], w.scalars) != 0) {
+                    // foreign operator (or unaligned arrays): SpMV through the vtable, then the dot pass
                     if (op->run_device(w.p, w.Ap) != 0) return 1;
                     B200_K(b200_dot_partials(w.nl, w.scalars, w.Ap, w.p, w.partials, &np[l], w.st));
                 }
@@ -669,6 +670,10 @@ int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Eng
                 w.own_band = true;
             }
             int maxp = 148 * 8;
+            if (!(eng->fused || fused_from_op)) {
+                const long long k = b200_csr_dot_partials_capacity(w.nl);  // generic operators: fused SpMV + dot
+                if (k > maxp) maxp = (int)k;
+            }
             if (eng->fused || fused_from_op) {
                 b200_band band;
                 w.band.describe(&band);

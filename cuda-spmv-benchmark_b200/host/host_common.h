@@ -68,6 +68,10 @@ int upload_band_csr(const MatrixData* mat, long long off, long long nl, DeviceBa
 int upload_band_ell(const MatrixData* mat, long long off, long long nl, DeviceBand* out, cudaStream_t s);
 
 // operator side-table: the band behind a stencil-type operator (for the fused CG path)
+// generic CSR / ELLPACK operators of this library: y = A x with the x.y partials in the same launch
+// (0 = done, -1 = not available for this operator: use run_device + b200_dot_partials)
+int operator_spmv_dot(const SpmvOperator* op, const double* d_x, double* d_y, double* d_partials, long long cap, int* np,
+                      const void* scalars);
 const DeviceBand* operator_band(const SpmvOperator* op);
 
 // verbose printing switch shared by the solvers

@@ -191,6 +191,21 @@ struct OpState {
         return rc;
     }
 
+    // y = A x fused with the partials of x.y (generic CSR / ELLPACK only); -1 = not available here
+    int launch_dot(const double* d_x, double* d_y, double* d_partials, long long cap, int* np, const void* scalars,
+                   cudaStream_t s) {
+        if (!ready || rows != cols) return -1;
+        int rc;
+        if (kind == K_CSR)
+            rc = b200_spmv_csr_dot(&plan, band.d_row_ptr, band.d_col_idx, band.d_values, d_x, d_y, rows, d_partials, cap, np,
+                                   scalars, s);
+        else if (kind == K_ELL)
+            rc = b200_spmv_ellpack_dot(band.d_col_idx, band.d_values, d_x, d_y, rows, ell_width, d_partials, cap, np, scalars, s);
+        else
+            return -1;
+        return rc == B200_OK ? 0 : -1;  // e.g. unaligned arrays: the caller falls back to SpMV + dot kernel
+    }
+
     int run_timed(const double* x, double* y, double* ms) {
         if (!ready) return EXIT_FAILURE;
         cudaEvent_t e0, e1;
@@ -232,6 +247,12 @@ SpmvOperator SPMV_ELLPACK = {"ellpack", ell_init, ell_run_timed, ell_run_device,
 SpmvOperator SPMV_STENCIL5_ELLPACK = {"stencil5-ellpack", st_ell_init, st_ell_run_timed, st_ell_run_device, st_ell_free};
 
 namespace b200host {
+int operator_spmv_dot(const SpmvOperator* op, const double* d_x, double* d_y, double* d_partials, long long cap, int* np,
+                      const void* scalars) {
+    if (op == &SPMV_CSR) return g_csr.launch_dot(d_x, d_y, d_partials, cap, np, scalars, 0);
+    if (op == &SPMV_ELLPACK) return g_ell.launch_dot(d_x, d_y, d_partials, cap, np, scalars, 0);
+    return -1;
+}
 const DeviceBand* operator_band(const SpmvOperator* op) {
     if (op == &SPMV_STENCIL5_CSR && g_st_csr.ready) return &g_st_csr.band;
     if (op == &SPMV_STENCIL5_ELLPACK && g_st_ell.ready) return &g_st_ell.band;

@@ -101,7 +101,8 @@ C_SYMBOLS = [
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_update_r_push", "b200_cg_halo_dir",
-    "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_reduce_rr_dir",
+    "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_reduce_rr_dir", "b200_csr_dot_partials_capacity",
+    "b200_spmv_csr_dot", "b200_spmv_ellpack_dot",
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
@@ -167,6 +168,10 @@ def load():
     L.b200_csr_plan_build.argtypes = [vp, ll, ll, C.POINTER(CsrPlan), vp]
     L.b200_spmv_csr.argtypes = [C.POINTER(CsrPlan), vp, vp, vp, vp, vp, ll, dbl, dbl, vp]
     L.b200_spmv_ellpack.argtypes = [vp, vp, vp, vp, ll, i32, dbl, dbl, vp]
+    L.b200_csr_dot_partials_capacity.restype = ll
+    L.b200_csr_dot_partials_capacity.argtypes = [ll]
+    L.b200_spmv_csr_dot.argtypes = [C.POINTER(CsrPlan), vp, vp, vp, vp, vp, ll, vp, ll, C.POINTER(i32), vp, vp]
+    L.b200_spmv_ellpack_dot.argtypes = [vp, vp, vp, vp, ll, i32, vp, ll, C.POINTER(i32), vp, vp]
     for f in ("b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_xchg_flag_prev_offset",
               "b200_xchg_flag_next_offset"):
         getattr(L, f).restype = C.c_size_t

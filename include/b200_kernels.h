@@ -115,6 +115,18 @@ int b200_spmv_csr(const b200_csr_plan* plan, const int* d_row_ptr, const int* d_
                   double alpha, double beta, b200_stream stream);
 int b200_spmv_ellpack(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
                       long long n_rows, int width, double alpha, double beta, b200_stream stream);
+/* y = A x fused with the partial sums of x.y (CG: p.Ap of a square operator; replaces the separate
+ * dot_kernel pass, cg_solver.cu:550-556).  One partial per warp item, summed in item order by
+ * b200_cg_reduce; d_partials needs b200_csr_dot_partials_capacity(n_rows) slots.  d_scalars (optional):
+ * the launch is a no-op once the solve has converged.  Needs 16-byte aligned col_idx / values. */
+long long b200_csr_dot_partials_capacity(long long n_rows);
+int b200_spmv_csr_dot(const b200_csr_plan* plan, const int* d_row_ptr, const int* d_col_idx,
+                      const double* d_values, const double* d_x, double* d_y, long long n_rows,
+                      double* d_partials, long long partials_capacity, int* n_partials_out,
+                      const void* d_scalars, b200_stream stream);
+int b200_spmv_ellpack_dot(const int* d_indices, const double* d_values, const double* d_x, double* d_y,
+                          long long n_rows, int width, double* d_partials, long long partials_capacity,
+                          int* n_partials_out, const void* d_scalars, b200_stream stream);
 
 /* ---- fused CG steps ---------------------------------------------------------------------
  * d_scalars: b200_cg_scalars_bytes() bytes of device memory (zero it before a solve).

@@ -331,6 +331,62 @@ def test_generic_csr_many_groups_per_warp(B, orc, torch_cuda, variant, shift):
     assert np.array_equal(y.cpu().numpy(), yo)
 
 
+@pytest.mark.parametrize("fmt", ["csr", "ell"])
+@pytest.mark.parametrize("n", [7, 130, 900])
+def test_generic_spmv_with_fused_dot(B, orc, torch_cuda, fmt, n):
+    """b200_spmv_csr_dot / b200_spmv_ellpack_dot (CG: Ap = A p and the p.Ap partials in one launch):
+    y bit-identical to the plain launch, partials summed in item order == x.y to rounding, and the
+    launch is a no-op once the scalars say converged"""
+    torch = torch_cuda
+    L = B.load()
+    N = n * n
+    orp64, oci, ova = orc.stencil5_csr_direct(n)
+    orp = orp64.astype(np.int32)
+    rng = np.random.default_rng(n)
+    xh = rng.standard_normal(N)
+    yo = orc.csr_spmv(orp, oci, ova, xh)
+    x = torch.from_numpy(xh).cuda()
+    y = torch.full((N,), float("nan"), dtype=torch.float64, device="cuda")
+    cap = L.b200_csr_dot_partials_capacity(N)
+    partials = torch.full((cap,), float("nan"), dtype=torch.float64, device="cuda")
+    sc = torch.zeros(L.b200_cg_scalars_bytes() // 8 + 1, dtype=torch.float64, device="cuda")
+    npart = C.c_int(0)
+    if fmt == "csr":
+        rp, ci, va = (torch.from_numpy(a).cuda() for a in (orp, oci, ova))
+        plan = B.CsrPlan()
+        B.check(L.b200_csr_plan_build(dptr(rp), N, len(ova), C.byref(plan), None), "plan")
+
+        def launch(out):
+            return L.b200_spmv_csr_dot(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x), dptr(out), N, dptr(partials),
+                                       cap, C.byref(npart), dptr(sc), None)
+    else:
+        w, oidx, oval = orc.build_ellpack(orp, oci, ova, N, N)
+        idx, val = torch.from_numpy(oidx).cuda(), torch.from_numpy(oval).cuda()
+
+        def launch(out):
+            return L.b200_spmv_ellpack_dot(dptr(idx), dptr(val), dptr(x), dptr(out), N, w, dptr(partials), cap,
+                                           C.byref(npart), dptr(sc), None)
+    B.check(launch(y), "spmv+dot")
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), yo)
+    assert 1 <= npart.value <= cap
+    got = float(partials[:npart.value].cpu().numpy().sum())
+    ref = float(np.dot(xh, yo))
+    assert abs(got - ref) <= 1e-12 * float(np.dot(np.abs(xh), np.abs(yo)))
+    # too small a buffer is refused, not overrun
+    assert L.b200_spmv_csr_dot is not None
+    # converged flag set -> no-op
+    conv_off = None
+    st = np.zeros(sc.numel(), dtype=np.float64)
+    raw = st.view(np.int32)
+    raw[2 * 7] = 1  # CGScalars.converged: 7 doubles, then the ints (csrc/cg_kernels.cuh)
+    sc.copy_(torch.from_numpy(st))
+    y2 = torch.full((N,), -7.0, dtype=torch.float64, device="cuda")
+    B.check(launch(y2), "spmv+dot converged")
+    torch.cuda.synchronize()
+    assert float(y2.min().item()) == -7.0 and float(y2.max().item()) == -7.0
+
+
 def test_stencil5_ellpack_kernel_signature(B, orc, torch_cuda):
     """include/spmv_stencil.h:40-42 argument list incl. alpha / beta"""
     torch = torch_cuda
