@@ -700,6 +700,58 @@ extern "C" int b200_cg_reduce_rr_dir(const double* d_partials, int n_partials, i
                          epoch, d_peer_xchg, d_stash, (d_r_prev || d_r_next) ? &h : nullptr, (cudaStream_t)stream);
 }
 
+// ---- Jacobi-preconditioned CG ----
+extern "C" int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
+                                 long long row_offset, int ell_width, double* d_dinv, int* d_err, b200_stream stream) {
+    if (!d_col_idx || !d_values || !d_dinv || !d_err || n_local < 0) return fail(B200_EINVAL, "pcg_diag_inv: bad argument");
+    if (!d_row_ptr && ell_width < 1) return fail(B200_EINVAL, "pcg_diag_inv: ELLPACK needs a width");
+    if (n_local == 0) return B200_OK;
+    pcg_diag_inv_kernel<<<blas1_grid(n_local, 1), 256, 0, (cudaStream_t)stream>>>(n_local, row_offset, d_row_ptr, ell_width,
+                                                                                 d_col_idx, d_values, d_dinv, d_err);
+    return check_launch("pcg_diag_inv_kernel");
+}
+
+extern "C" int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, double* d_partials,
+                             int* n_partials_out, b200_stream stream) {
+    if (!d_r || !d_dinv || !d_p || !d_partials) return fail(B200_EINVAL, "pcg_init: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    if (n_partials_out) *n_partials_out = grid;
+    pcg_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_r, d_dinv, d_p, d_partials);
+    return check_launch("pcg_init_kernel");
+}
+
+extern "C" int b200_pcg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
+                                  const double* d_dinv, double* d_x, double* d_r, double* d_partials_rr,
+                                  double* d_partials_rz, int* n_partials_out, b200_stream stream) {
+    if (!d_scalars || !d_p || !d_Ap || !d_dinv || !d_x || !d_r || !d_partials_rr || !d_partials_rz)
+        return fail(B200_EINVAL, "pcg_update_xr: NULL argument");
+    const int grid = blas1_grid(n, 1);
+    if (n_partials_out) *n_partials_out = grid;
+    pcg_update_xr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_p, d_Ap, d_dinv,
+                                                                 d_x, d_r, d_partials_rr, d_partials_rz);
+    return check_launch("pcg_update_xr_kernel");
+}
+
+extern "C" int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
+                                 b200_stream stream) {
+    if (!d_scalars || !d_r || !d_dinv || !d_p) return fail(B200_EINVAL, "pcg_update_p: NULL argument");
+    pcg_update_p_kernel<<<blas1_grid(n, 1), 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_r,
+                                                                            d_dinv, d_p);
+    return check_launch("pcg_update_p_kernel");
+}
+
+extern "C" int b200_pcg_reduce(const double* d_partials_rr, const double* d_partials_rz, int n_partials, double tol,
+                               void* d_scalars, void* h_status_mapped, b200_stream stream) {
+    if (!d_partials_rr || !d_partials_rz || n_partials < 0 || !d_scalars) return fail(B200_EINVAL, "pcg_reduce: bad argument");
+    ReduceArgs a;
+    memset(&a, 0, sizeof a);
+    a.partials = d_partials_rr; a.partials_b = d_partials_rz; a.n_partials = n_partials; a.which = RED_PCG; a.phases = 3;
+    a.tol = tol; a.sc = static_cast<CGScalars*>(d_scalars); a.status = static_cast<CGStatus*>(h_status_mapped);
+    a.rank = 0; a.world = 1;
+    cg_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("cg_reduce_kernel");
+}
+
 extern "C" int b200_dot_partials(long long n, const void* d_scalars, const double* d_x, const double* d_y,
                                  double* d_partials, int* n_partials_out, b200_stream stream) {
     if (!d_x || !d_y || !d_partials) return fail(B200_EINVAL, "dot_partials: NULL argument");

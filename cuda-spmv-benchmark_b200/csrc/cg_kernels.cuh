@@ -80,11 +80,12 @@ struct HaloDirArgs {
     int beta_zero;
 };
 
-enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3 };
+enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3, RED_RZ0 = 4, RED_PCG = 5 };  // 4, 5: Jacobi PCG
 enum { RED_PUSH = 1, RED_COMBINE = 2 };
 
 struct ReduceArgs {
     const double* partials;
+    const double* partials_b;  // RED_PCG: the r.z partials (partials = r.r), same count; single rank only
     int n_partials;
     int which;   // RED_*
     int phases;  // RED_PUSH | RED_COMBINE
@@ -116,12 +117,20 @@ __global__ void __launch_bounds__(1024) cg_reduce_kernel(const ReduceArgs a) {
     if (a.which != RED_SUM && sc->converged) return;
 
     const int t = threadIdx.x;
+    __shared__ double local_total_b;
     if (a.phases & RED_PUSH) {
         double v = 0.0;
         for (int i = t; i < a.n_partials; i += 1024) v += a.partials[i];
         v = block_sum(v, scratch);
         if (t == 0) { local_total = v; if (a.stash) *a.stash = v; }
         __syncthreads();
+        if (a.which == RED_PCG) {
+            double w = 0.0;
+            for (int i = t; i < a.n_partials; i += 1024) w += a.partials_b[i];
+            w = block_sum(w, scratch);
+            if (t == 0) local_total_b = w;
+            __syncthreads();
+        }
         if (a.world > 1 && t < a.world) {
             const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
             const uint64_t tag = (uint64_t)a.epoch << 32;
@@ -172,7 +181,27 @@ __global__ void __launch_bounds__(1024) cg_reduce_kernel(const ReduceArgs a) {
             if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
         } else if (a.which == RED_PAP) {
             sc->pAp = total;
-            sc->alpha = sc->rr_old / total;
+            sc->alpha = sc->rr_old / total;  // PCG keeps rho = r.z in rr_old
+        } else if (a.which == RED_RZ0) {
+            sc->rr_old = total;  // rho_0 = r0.z0 (b_norm was set by RED_RR0)
+        } else if (a.which == RED_PCG) {
+            sc->rr_new = total;
+            const double res = sqrt(total);
+            sc->residual = res;
+            const int it = sc->iterations + 1;
+            sc->iterations = it;
+            const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
+            if (conv) {
+                sc->converged = 1;
+            } else {
+                sc->beta = local_total_b / sc->rr_old;
+                sc->rr_old = local_total_b;
+            }
+            if (a.status) {
+                a.status->residual = res;
+                a.status->iterations = it;
+                a.status->converged = conv;
+            }
         } else {  // RED_RR
             sc->rr_new = total;
             const double res = sqrt(total);
@@ -450,6 +479,107 @@ __global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGS
                 const long long i = base + (long long)u * 256 + threadIdx.x;
                 if (i < n) p[i] = fma(beta, p[i], r[i]);
             }
+        }
+    }
+}
+
+// ---- Jacobi-preconditioned CG (not in the reference: its README lists preconditioning as the next step) ----
+// z = D^-1 r is never stored: K2p forms it for the r.z partials, K3p forms it again for p = z + beta p.
+// dinv[i] = 1 / A(i,i) from the CSR / ELLPACK arrays (row_ptr == NULL: ELLPACK of width `width`);
+// *err is set when a row has no (or a zero) diagonal entry.
+__global__ void __launch_bounds__(256) pcg_diag_inv_kernel(long long n_local, long long row_offset,
+                                                           const int* __restrict__ row_ptr, int width,
+                                                           const int* __restrict__ col_idx,
+                                                           const double* __restrict__ values,
+                                                           double* __restrict__ dinv, int* __restrict__ err) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_local; i += (long long)gridDim.x * 256) {
+        const long long s = row_ptr ? row_ptr[i] : i * width, e = row_ptr ? row_ptr[i + 1] : (i + 1) * width;
+        const unsigned int want = (unsigned int)(row_offset + i);  // columns are stored modulo 2^32
+        double d = 0.0;
+        for (long long k = s; k < e; k++)
+            if ((unsigned int)col_idx[k] == want && (row_ptr || col_idx[k] >= 0)) d = values[k];
+        if (d == 0.0) { *err = 1; dinv[i] = 0.0; }
+        else dinv[i] = 1.0 / d;
+    }
+}
+
+// after the residual init (r = b - A x0): p0 = z0 = dinv r0, partials of rho_0 = r0.z0
+__global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double* __restrict__ r,
+                                                       const double* __restrict__ dinv, double* __restrict__ p,
+                                                       double* __restrict__ partials) {
+    __shared__ double scratch[8];
+    double acc = 0.0;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) {
+                const double rv = r[i], z = dinv[i] * rv;
+                p[i] = z;
+                acc = fma(rv, z, acc);
+            }
+        }
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// K2p: x += alpha p ; r -= alpha Ap ; partials of r.r (convergence) and r.z (rho), z = dinv r
+__global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                            const double* __restrict__ p,
+                                                            const double* __restrict__ Ap,
+                                                            const double* __restrict__ dinv, double* __restrict__ x,
+                                                            double* __restrict__ r, double* __restrict__ partials_rr,
+                                                            double* __restrict__ partials_rz) {
+    __shared__ double scratch[8];
+    if (sc->converged) return;
+    const double alpha = sc->alpha, nalpha = -alpha;
+    double arr = 0.0, arz = 0.0;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        double pv[4], av[4], xv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) { pv[u] = __ldcs(p + i); av[u] = __ldcs(Ap + i); xv[u] = __ldcs(x + i); rv[u] = __ldcs(r + i); dv[u] = __ldcs(dinv + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) {
+                x[i] = fma(alpha, pv[u], xv[u]);
+                const double rn = fma(nalpha, av[u], rv[u]);
+                r[i] = rn;
+                arr = fma(rn, rn, arr);
+                arz = fma(rn, dv[u] * rn, arz);
+            }
+        }
+    }
+    arr = block_sum(arr, scratch);
+    __syncthreads();
+    arz = block_sum(arz, scratch);
+    if (threadIdx.x == 0) { partials_rr[blockIdx.x] = arr; partials_rz[blockIdx.x] = arz; }
+}
+
+// K3p: p = z + beta p, z = dinv r
+__global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                           const double* __restrict__ r,
+                                                           const double* __restrict__ dinv, double* __restrict__ p) {
+    if (sc->converged) return;
+    const double beta = sc->beta;
+    const long long tile = 1024;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        double pv[4], rv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) { pv[u] = __ldcs(p + i); rv[u] = __ldcs(r + i); dv[u] = __ldcs(dinv + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long i = base + u * 256 + threadIdx.x;
+            if (i < n) p[i] = fma(beta, pv[u], dv[u] * rv[u]);
         }
     }
 }

@@ -181,6 +181,8 @@ struct RankWs {
     bool own_band = false;
     double *x = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *Ap = nullptr, *b = nullptr;
     double *partials = nullptr, *partials2 = nullptr, *stash = nullptr, *sums = nullptr;
+    double* dinv = nullptr;  // Jacobi PCG: 1 / diag(A), allocated on first use
+    int* dinv_err = nullptr;
     void* scalars = nullptr;
     HostStatus* status = nullptr;  // pinned + mapped
     void* status_dev = nullptr;
@@ -193,6 +195,8 @@ struct RankWs {
     void free_vectors() {
         cudaFree(x); cudaFree(r); cudaFree(p); cudaFree(p2); cudaFree(Ap); cudaFree(b);
         cudaFree(partials); cudaFree(partials2); cudaFree(stash); cudaFree(sums); cudaFree(scalars);
+        cudaFree(dinv); cudaFree(dinv_err);
+        dinv = nullptr; dinv_err = nullptr;
         x = r = p = p2 = Ap = b = partials = partials2 = stash = sums = nullptr;
         scalars = nullptr;
         if (status) cudaFreeHost((void*)status);
@@ -327,6 +331,7 @@ namespace {
 
 struct Engine {
     bool fused;           // band kernels available (stencil operators / mgpu); else op->run_device
+    bool pcg = false;     // Jacobi-preconditioned CG (single GPU, classic launch grouping)
     SpmvOperator* op;     // generic path
     int n_partials_spmv[kMaxRanks];
 
@@ -372,6 +377,27 @@ struct Engine {
             B200_CUDA(cudaMemcpyAsync(w.b, b_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
             B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
         }
+        if (pcg) {
+            // untimed set-up like the uploads: dinv = 1 / diag(A), rebuilt for every solve (the matrix
+            // behind an operator may have changed while the shape stayed the same)
+            if (multi) { fprintf(stderr, "[ERROR] Jacobi PCG is single-GPU\n"); return 1; }
+            RankWs& w = ws.ranks[0];
+            int ell_width = 0;
+            const DeviceBand* m = fused ? &w.band : operator_matrix(op, &ell_width);
+            if (!m) { fprintf(stderr, "[ERROR] Jacobi PCG needs one of this library's operators (diagonal access)\n"); return 1; }
+            if (m->layout == 1 && ell_width == 0) ell_width = 5;  // stencil ELLPACK band
+            if (!w.dinv) {
+                B200_CUDA(cudaMalloc(&w.dinv, (size_t)w.nl * sizeof(double)));
+                B200_CUDA(cudaMalloc(&w.dinv_err, sizeof(int)));
+            }
+            B200_CUDA(cudaMemsetAsync(w.dinv_err, 0, sizeof(int), w.st));
+            B200_K(b200_pcg_diag_inv(m->layout == 0 ? m->d_row_ptr : nullptr, m->d_col_idx, m->d_values, w.nl, w.off, ell_width,
+                                     w.dinv, w.dinv_err, w.st));
+            int bad = 0;
+            B200_CUDA(cudaMemcpyAsync(&bad, w.dinv_err, sizeof(int), cudaMemcpyDeviceToHost, w.st));
+            B200_CUDA(cudaStreamSynchronize(w.st));
+            if (bad) { fprintf(stderr, "[ERROR] Jacobi PCG: a row has no (or a zero) diagonal entry\n"); return 1; }
+        }
         for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
         if (multi) {
             // Align the ranks before the clock starts (the reference does MPI_Barrier right before its
@@ -414,6 +440,11 @@ struct Engine {
         if (for_ranks_reduce(0, tol, np, false, ++g.red_epoch)) return 1;
         B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
         pt.mark(T_RED_RR0);
+        if (pcg) {  // p0 = z0 = D^-1 r0, rho_0 = r0.z0
+            RankWs& w = ws.ranks[0];
+            B200_K(b200_pcg_init(w.nl, w.r, w.dinv, w.p, w.partials, &np[0], w.st));
+            if (for_ranks_reduce(4, tol, np, false, ++g.red_epoch)) return 1;
+        }
         if (multi) {
             const uint32_t e = ++g.halo_epoch;
             for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_K(push_halo(w, w.p, e, nullptr)); }
@@ -429,7 +460,7 @@ struct Engine {
 
         // ---- iterations (cg_solver.cu:538-638)
         const int lag = verbose >= 2 ? 0 : kLag;
-        const bool dx = fused && schedule_deferred_x();
+        const bool dx = fused && schedule_deferred_x() && !pcg;
         if (multi && dx) {
             // first direction: p0 = r0, its edges are in the landing buffers (pushed above)
             for (auto& w : ws.ranks) {
@@ -501,6 +532,9 @@ struct Engine {
                         B200_K(b200_cg_update_r(w.nl, w.scalars, w.Ap, w.r, w.partials2, &np[l], w.st));
                     }
                 }
+            } else if (pcg) {  // K2p: + partials r.z with z = D^-1 r
+                RankWs& w = ws.ranks[0];
+                B200_K(b200_pcg_update_xr(w.nl, w.scalars, w.p, w.Ap, w.dinv, w.x, w.r, w.partials2, w.partials, &np[0], w.st));
             } else {
                 for (size_t l = 0; l < L; l++) {  // K2: x += alpha p, r -= alpha Ap, partials r.r
                     RankWs& w = ws.ranks[l];
@@ -514,13 +548,19 @@ struct Engine {
             nvtxRangePushA("Dot_Product");
             // convergence, beta; multi-GPU deferred-x: + halo copies of the next direction,
             // p_halo = r_halo + beta p_halo_old (the r edges were pushed by K2r above)
-            if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch, (dx && multi) ? it : -1)) return 1;
+            if (pcg) {
+                RankWs& w = ws.ranks[0];
+                B200_K(b200_pcg_reduce(w.partials2, w.partials, np[0], tol, w.scalars, w.status_dev, w.st));
+            } else if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch, (dx && multi) ? it : -1)) return 1;
             nvtxRangePop();
             B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
             pt.mark(T_RED_RR);
             if (!dx) {
                 Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
-                if (!multi) {
+                if (pcg) {  // K3p: p = D^-1 r + beta p
+                    RankWs& w = ws.ranks[0];
+                    B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, w.st));
+                } else if (!multi) {
                     for (auto& w : ws.ranks) {  // K3: p = r + beta p
                         B200_CUDA(cudaSetDevice(w.dev));
                         B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
@@ -640,7 +680,8 @@ int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Eng
     const void* key = (fused_from_op || !eng->fused) ? (const void*)op : (const void*)nullptr;
     bool same = ws.N == N && ws.grid == mat->grid_size && ws.world == g.world && ws.matrix_key == key &&
                 ws.matrix_nnz == mat->nnz && !ws.ranks.empty();
-    if (same && fused_from_op) same = ws.ranks[0].band.d_values == operator_band(op)->d_values;
+    // (a band borrowed from an operator is re-read below on every call: the operator may have been
+    // freed and re-initialised between two solves, and any of its three arrays may have moved)
     if (same && !fused_from_op && eng->fused) same = is_synthetic(mat) && ws.synthetic;
     if (!same) {
         ws.release();
@@ -685,6 +726,12 @@ int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Eng
         }
     }
     for (size_t l = 0; l < ws.ranks.size(); l++) {
+        if (fused_from_op) {
+            const DeviceBand* ob = operator_band(op);
+            if (!ob || ob->n_local != ws.ranks[l].nl) return 1;
+            ws.ranks[l].band = *ob;  // current device arrays of the operator (never owned here)
+            ws.ranks[l].own_band = false;
+        }
         if (eng->fused || fused_from_op) {
             b200_band band;
             ws.ranks[l].band.describe(&band);
@@ -721,7 +768,7 @@ void print_summary(const char* tag, const CGStats* s) {
 }
 
 int solve_single(SpmvOperator* op, MatrixData* mat, const double* b, double* x, CGConfig cfg, CGStats* stats,
-                 const char* tag) {
+                 const char* tag, bool pcg = false) {
     if (!op || !mat || !b || !x || !stats) return 1;
     if (!op->run_device) {
         fprintf(stderr, "[ERROR] Operator '%s' does not support device-native interface\n", op->name);
@@ -737,6 +784,7 @@ int solve_single(SpmvOperator* op, MatrixData* mat, const double* b, double* x, 
     const bool fused_from_op = operator_band(op) != nullptr;
     if (prepare_workspace(mat, op, fused_from_op, &eng)) return 1;
     eng.fused = fused_from_op;
+    eng.pcg = pcg;
     SolveOut o;
     int rc = eng.solve(b, x, cfg.max_iters, cfg.tolerance, cfg.verbose, cfg.enable_detailed_timers, tag, &o);
     if (rc) return rc;
@@ -751,6 +799,13 @@ int solve_single(SpmvOperator* op, MatrixData* mat, const double* b, double* x, 
 int cg_solve_device(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x, CGConfig config,
                     CGStats* stats) {
     return solve_single(spmv_op, mat, b, x, config, stats, "CG-DEVICE");
+}
+
+// Jacobi-preconditioned CG, M = diag(A).  Not in the reference (cg_solver.h:6-7 names preconditioning
+// as future work); same argument list, conventions and statistics as cg_solve_device.
+int pcg_solve_device(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x, CGConfig config,
+                     CGStats* stats) {
+    return solve_single(spmv_op, mat, b, x, config, stats, "PCG-DEVICE", true);
 }
 
 // Host-interface variant.  The reference runs the same recurrence but round-trips every SpMV

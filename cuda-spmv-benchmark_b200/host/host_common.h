@@ -73,6 +73,7 @@ int upload_band_ell(const MatrixData* mat, long long off, long long nl, DeviceBa
 int operator_spmv_dot(const SpmvOperator* op, const double* d_x, double* d_y, double* d_partials, long long cap, int* np,
                       const void* scalars);
 const DeviceBand* operator_band(const SpmvOperator* op);
+const DeviceBand* operator_matrix(const SpmvOperator* op, int* ell_width);
 
 // verbose printing switch shared by the solvers
 extern int g_quiet;

@@ -253,6 +253,14 @@ int operator_spmv_dot(const SpmvOperator* op, const double* d_x, double* d_y, do
     if (op == &SPMV_ELLPACK) return g_ell.launch_dot(d_x, d_y, d_partials, cap, np, scalars, 0);
     return -1;
 }
+// device matrix of any of this library's four operators (Jacobi PCG reads the diagonal from it)
+const DeviceBand* operator_matrix(const SpmvOperator* op, int* ell_width) {
+    const OpState* st = op == &SPMV_CSR ? &g_csr : op == &SPMV_ELLPACK ? &g_ell : op == &SPMV_STENCIL5_CSR ? &g_st_csr
+                        : op == &SPMV_STENCIL5_ELLPACK ? &g_st_ell : nullptr;
+    if (!st || !st->ready) return nullptr;
+    if (ell_width) *ell_width = st->ell_width;
+    return &st->band;
+}
 const DeviceBand* operator_band(const SpmvOperator* op) {
     if (op == &SPMV_STENCIL5_CSR && g_st_csr.ready) return &g_st_csr.band;
     if (op == &SPMV_STENCIL5_ELLPACK && g_st_ell.ready) return &g_st_ell.band;

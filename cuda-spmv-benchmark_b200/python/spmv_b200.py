@@ -102,7 +102,8 @@ C_SYMBOLS = [
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_update_r_push", "b200_cg_halo_dir",
     "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_reduce_rr_dir", "b200_csr_dot_partials_capacity",
-    "b200_spmv_csr_dot", "b200_spmv_ellpack_dot",
+    "b200_spmv_csr_dot", "b200_spmv_ellpack_dot", "b200_pcg_diag_inv", "b200_pcg_init", "b200_pcg_update_xr",
+    "b200_pcg_update_p", "b200_pcg_reduce",
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
@@ -126,6 +127,7 @@ CXX_SYMBOLS = {
     "build_ellpack_from_csr_struct": "_Z29build_ellpack_from_csr_structPK9CSRMatrixP13ELLPACKMatrixPi",
     "cg_solve": "_Z8cg_solveP12SpmvOperatorP10MatrixDataPKdPd8CGConfigP7CGStats",
     "cg_solve_device": "_Z15cg_solve_deviceP12SpmvOperatorP10MatrixDataPKdPd8CGConfigP7CGStats",
+    "pcg_solve_device": "_Z16pcg_solve_deviceP12SpmvOperatorP10MatrixDataPKdPd8CGConfigP7CGStats",
     "cg_solve_mgpu": "_Z13cg_solve_mgpuP12SpmvOperatorP10MatrixDataPKdPd16CGConfigMultiGPUP15CGStatsMultiGPU",
     "cg_solve_mgpu_partitioned":
         "_Z25cg_solve_mgpu_partitionedP12SpmvOperatorP10MatrixDataPKdPd16CGConfigMultiGPUP15CGStatsMultiGPU",
@@ -241,7 +243,7 @@ def load():
     L.build_csr_struct.argtypes = [C.POINTER(MatrixData)]
     L.build_ellpack_from_csr_struct = getattr(L, CXX_SYMBOLS["build_ellpack_from_csr_struct"])
     L.build_ellpack_from_csr_struct.argtypes = [C.POINTER(CSRMatrix), C.POINTER(ELLPACKMatrix), C.POINTER(i32)]
-    for nm in ("cg_solve", "cg_solve_device"):
+    for nm in ("cg_solve", "cg_solve_device", "pcg_solve_device"):
         f = getattr(L, CXX_SYMBOLS[nm])
         f.argtypes = [C.POINTER(SpmvOperator), C.POINTER(MatrixData), vp, vp, CGConfig, C.POINTER(CGStats)]
         setattr(L, nm, f)

@@ -96,6 +96,10 @@ int cg_solve(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
              CGStats* stats);
 int cg_solve_device(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x, CGConfig config,
                     CGStats* stats);
+/* extension (the reference lists preconditioning as future work, cg_solver.h:6-7):
+ * Jacobi-preconditioned CG, M = diag(A); arguments, conventions and statistics of cg_solve_device */
+int pcg_solve_device(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x, CGConfig config,
+                     CGStats* stats);
 int cg_solve_mgpu(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
                   CGConfigMultiGPU config, CGStatsMultiGPU* stats);
 int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,

@@ -221,6 +221,22 @@ int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, con
 /* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 5-launch schedule;
  * the environment variable B200_CG_SCHEDULE=classic selects 0 at start-up */
 void b200_cg_set_schedule(int deferred_x);
+/* ---- Jacobi-preconditioned CG (single GPU) --------------------------------------------------
+ * Not in the reference (its cg_solver.h:6-7 / README name preconditioning as the next step): the
+ * textbook recurrence over the conventions of cg_solve_device (cg_solver.cu:498-638).  z = D^-1 r is
+ * never stored.  rho = r.z lives in the scalar block where plain CG keeps r.r, so b200_cg_spmv_dot /
+ * b200_cg_reduce(which = 1) serve unchanged; b200_cg_reduce(which = 4) stores rho_0.               */
+int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
+                      long long row_offset, int ell_width, double* d_dinv, int* d_err, b200_stream stream);
+int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, double* d_partials,
+                  int* n_partials_out, b200_stream stream);
+int b200_pcg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
+                       const double* d_dinv, double* d_x, double* d_r, double* d_partials_rr,
+                       double* d_partials_rz, int* n_partials_out, b200_stream stream);
+int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
+                      b200_stream stream);
+int b200_pcg_reduce(const double* d_partials_rr, const double* d_partials_rz, int n_partials, double tol,
+                    void* d_scalars, void* h_status_mapped, b200_stream stream);
 /* offsets of the halo flags inside an exchange area */
 size_t b200_xchg_flag_prev_offset(void);
 size_t b200_xchg_flag_next_offset(void);

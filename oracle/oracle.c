@@ -417,6 +417,68 @@ int orc_cg_device(const orc_csr* A, int grid, int op, const double* b, double* x
 /* partition                                                           */
 /* ------------------------------------------------------------------ */
 
+/* Jacobi-preconditioned CG.  NOT in the reference (its README / cg_solver.h:6-7 list preconditioning
+ * as the next step; parity unpinned): the textbook recurrence laid over the reference's CG conventions
+ * (cg_solver.cu:498-638): r0 = b - A x0, z = D^-1 r, p0 = z0, rho = r.z; per iteration alpha = rho / p.Ap,
+ * x += alpha p, r -= alpha Ap, stop when ||r|| / ||r0|| < tol (checked before the p update, iterations
+ * counted like cg_solve_device), z = D^-1 r, beta = rho_new / rho, p = z + beta p.  D = diag(A). */
+int orc_pcg_device(const orc_csr* A, int grid, int op, const double* b, double* x, int max_iters,
+                   double tol, orc_cg_result* res) {
+    int n = A->nb_rows;
+    double* r = (double*)malloc((size_t)n * sizeof(double));
+    double* z = (double*)malloc((size_t)n * sizeof(double));
+    double* p = (double*)malloc((size_t)n * sizeof(double));
+    double* Ap = (double*)malloc((size_t)n * sizeof(double));
+    double* dinv = (double*)malloc((size_t)n * sizeof(double));
+    if (!r || !z || !p || !Ap || !dinv) return 1;
+    for (int i = 0; i < n; i++) {
+        double d = 0.0;
+        for (int k = A->row_ptr[i]; k < A->row_ptr[i + 1]; k++)
+            if (A->col_indices[k] == i) d = A->values[k];
+        if (d == 0.0) { free(r); free(z); free(p); free(Ap); free(dinv); return 2; }
+        dinv[i] = 1.0 / d;
+    }
+    apply_op(A, grid, op, x, Ap);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) { r[i] = fma(1.0, b[i], -1.0 * Ap[i]); z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+    double rr0 = orc_dot_blocktree(n, r, r);
+    double rho = orc_dot_blocktree(n, r, z);
+    double b_norm = sqrt(rr0);
+    double final_res = b_norm;
+    int iter;
+    for (iter = 0; iter < max_iters; iter++) {
+        apply_op(A, grid, op, p, Ap);
+        double pAp = orc_dot_blocktree(n, Ap, p);
+        double alpha = rho / pAp;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) {
+            x[i] = fma(alpha, p[i], x[i]);
+            r[i] = fma(-alpha, Ap[i], r[i]);
+            z[i] = dinv[i] * r[i];
+        }
+        double rr_new = orc_dot_blocktree(n, r, r);
+        double rho_new = orc_dot_blocktree(n, r, z);
+        double resn = sqrt(rr_new);
+        final_res = resn;
+        if (resn / b_norm < tol) { iter++; break; }
+        double beta = rho_new / rho;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) p[i] = fma(beta, p[i], z[i]);
+        rho = rho_new;
+    }
+    res->iterations = iter;
+    res->residual_norm = final_res;
+    res->b_norm = b_norm;
+    res->converged = (final_res / b_norm < tol) ? 1 : 0;
+    double s = 0.0, s2 = 0.0;
+    for (int i = 0; i < n; i++) { s += x[i]; s2 += x[i] * x[i]; }
+    res->solution_sum = s;
+    res->solution_norm = sqrt(s2);
+    free(r); free(z); free(p); free(Ap); free(dinv);
+    return 0;
+}
+
+
 /* src/solvers/cg_solver_mgpu_partitioned.cu:262-268: n_local = N / P (matrix rows),
  * row_offset = g * n_local, the last rank takes N - row_offset. */
 void orc_partition(int64_t N, int P, int g, int64_t* n_local, int64_t* row_offset) {

@@ -101,6 +101,9 @@ double orc_dot_sequential(int n, const double* x, const double* y);
 /* op: 0 = generic CSR (sequential-k), 1 = stencil5 csr-direct order */
 int orc_cg_device(const orc_csr* A, int grid, int op, const double* b, double* x, int max_iters,
                   double tol, orc_cg_result* res, double* rel_hist, int rel_hist_cap);
+/* Jacobi-preconditioned CG (not in the reference: parity unpinned), same conventions as orc_cg_device */
+int orc_pcg_device(const orc_csr* A, int grid, int op, const double* b, double* x, int max_iters,
+                   double tol, orc_cg_result* res);
 int orc_cg_mgpu(const orc_csr* A, int grid, int P, const double* b, double* x, int max_iters,
                 double tol, orc_cg_result* res);
 
