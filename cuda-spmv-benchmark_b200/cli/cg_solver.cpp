@@ -1,4 +1,5 @@
 // cg_solver <file.mtx | --grid=n> [--mode=a[,b]] [--host] [--tol=] [--maxiter=] [--timers] [--json=] [--csv=]
+//           [--precond=jacobi]   (extension: Jacobi-preconditioned CG, pcg_solve_device)
 // reference src/main/cg_solver.cu:23-243: defaults stencil5-csr / device path / tol 1e-6 / 1000 it,
 // b = 1, x0 = 0, 3 warm-up solves, cg_benchmark_with_stats_device(10), "<json>_<mode>.json", CSV appended.
 #include "cli_common.h"
@@ -7,7 +8,7 @@ int main(int argc, char** argv) {
     CliArgs a = parse_cli(argc, argv);
     if (a.matrix.empty() && a.grid <= 0) {
         fprintf(stderr, "Usage: %s <matrix.mtx | --grid=n> [--mode=<m1[,m2]>] [--host] [--tol=<t>] [--maxiter=<n>] "
-                        "[--timers] [--json=<file>] [--csv=<file>]\n", argv[0]);
+                        "[--timers] [--json=<file>] [--csv=<file>] [--precond=jacobi]\n", argv[0]);
         return EXIT_FAILURE;
     }
     if (a.modes.empty()) a.modes.push_back("stencil5-csr");
@@ -33,13 +34,33 @@ int main(int argc, char** argv) {
         printf("Warmup (3 runs)...\n");
         for (int w = 0; w < 3; w++) {
             std::fill(x.begin(), x.end(), 0.0);
-            int rc = a.host ? cg_solve(op, &mat, b.data(), x.data(), quiet, &st) : cg_solve_device(op, &mat, b.data(), x.data(), quiet, &st);
+            int rc = a.jacobi ? pcg_solve_device(op, &mat, b.data(), x.data(), quiet, &st)
+                     : a.host ? cg_solve(op, &mat, b.data(), x.data(), quiet, &st)
+                              : cg_solve_device(op, &mat, b.data(), x.data(), quiet, &st);
             if (rc != 0) { fprintf(stderr, "CG solve failed\n"); return EXIT_FAILURE; }
         }
         std::fill(x.begin(), x.end(), 0.0);
         printf("Running benchmark (%d runs)...\n", a.runs);
         BenchmarkStats bs;
-        if (cg_benchmark_with_stats_device(op, &mat, b.data(), x.data(), cfg, a.runs, &bs, &st) != 0) {
+        if (a.jacobi) {
+            // no reference wrapper exists for the preconditioned solver: same protocol (runs solves from
+            // x0 = 0, median of the solver's own device time), statistics without the outlier filter
+            std::vector<double> t;
+            for (int r = 0; r < a.runs; r++) {
+                std::fill(x.begin(), x.end(), 0.0);
+                if (pcg_solve_device(op, &mat, b.data(), x.data(), quiet, &st) != 0) { fprintf(stderr, "PCG solve failed\n"); return EXIT_FAILURE; }
+                t.push_back(st.time_total_ms);
+            }
+            std::sort(t.begin(), t.end());
+            memset(&bs, 0, sizeof bs);
+            double sum = 0, sq = 0;
+            for (double v : t) sum += v;
+            bs.valid_runs = (int)t.size(); bs.min_ms = t.front(); bs.max_ms = t.back(); bs.median_ms = t[t.size() / 2];
+            bs.mean_ms = sum / t.size();
+            for (double v : t) sq += (v - bs.mean_ms) * (v - bs.mean_ms);
+            bs.std_dev_ms = t.size() > 1 ? sqrt(sq / (t.size() - 1)) : 0.0;
+            printf("(Jacobi-preconditioned CG)\n");
+        } else if (cg_benchmark_with_stats_device(op, &mat, b.data(), x.data(), cfg, a.runs, &bs, &st) != 0) {
             fprintf(stderr, "CG benchmark failed for mode '%s'\n", op->name);
             return EXIT_FAILURE;
         }

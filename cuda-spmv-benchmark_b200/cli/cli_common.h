@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@ struct CliArgs {
     double tol = 1e-6;
     int maxiter = 1000;
     bool timers = false, host = false;
+    bool jacobi = false;                // --precond=jacobi (cg_solver only; extension)
     int runs = 10;
 };
 
@@ -50,6 +52,7 @@ inline CliArgs parse_cli(int argc, char** argv) {
         else if (starts(s, "--runs=")) a.runs = atoi(s + 7);
         else if (!strcmp(s, "--timers")) a.timers = true;
         else if (!strcmp(s, "--host")) a.host = true;
+        else if (!strcmp(s, "--precond=jacobi")) a.jacobi = true;
         else if (s[0] != '-' && a.matrix.empty()) a.matrix = s;
     }
     return a;

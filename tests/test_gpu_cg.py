@@ -315,3 +315,27 @@ def test_pcg_rejects_missing_diagonal(B, orc, torch_cuda):
     x, st = np.zeros(N), B.CGStats()
     assert L.pcg_solve_device(op, hm.ptr(), np.ones(N).ctypes.data, x.ctypes.data, B.cg_config(), C.byref(st)) != 0
     op.contents.free()
+
+
+@pytest.mark.parametrize("n", [130, 258, 274, 300])
+def test_cg_operator_reinit_between_solves(B, orc, torch_cuda, n):
+    """regression: a workspace re-used after op.free() + op.init() must pick up the operator's NEW
+    device arrays (all three may move); stale row_ptr / col_idx pointers showed up as wrong boundary
+    rows in one solve out of a few.  Six solves with re-initialisation in between, both schedules,
+    each checked against the oracle after 2 iterations."""
+    L = B.load()
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(n)
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    xo, ro, _ = oracle_solve(orc, n, 1, b, x0, max_iters=2)
+    try:
+        for k in range(6):
+            L.b200_cg_set_schedule(k & 1)
+            x, st, op = solve_device(B, b"stencil5-csr", hm, b, x0, max_iters=2)
+            op.contents.free()
+            assert st["iterations"] == 2
+            assert abs(st["residual_norm"] - ro["residual_norm"]) <= 1e-10 * ro["residual_norm"], (k, n)
+            assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-12
+    finally:
+        L.b200_cg_set_schedule(1)
