@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Randomised parity stress (development tool, complements tests/): random grid sizes, bands, tuning
+variants, row-length mixes and CG schedules against the CPU oracle, through the C ABI.
+
+  python tools/stress.py [--seconds 90] [--seed 0]
+Prints one line per failing case and a summary; exit code 1 if anything failed."""
+import argparse
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "cuda-spmv-benchmark_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import torch  # noqa: E402
+
+import orc  # noqa: E402
+import spmv_b200 as B  # noqa: E402
+
+dp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stencil_case(L, rng):
+    n = int(rng.integers(1, 420))
+    N = n * n
+    P = int(rng.integers(1, 6))
+    variant, R = int(rng.integers(0, 14)), int(rng.choice([0, 1, 3, 4, 8, 16, 33]))
+    xh = rng.standard_normal(N)
+    rp64, oci, ova = orc.stencil5_csr_direct(n)
+    y_full = orc.stencil5_spmv(rp64.astype(np.int32), oci, ova, xh, n)
+    if N // P < n:
+        P = 1
+    for g in range(P):
+        nl, off = orc.partition(N, P, g)
+        lnnz = L.b200_stencil5_nnz_before(off + nl, n) - L.b200_stencil5_nnz_before(off, n)
+        rp = torch.empty(nl + 1, dtype=torch.int32, device="cuda")
+        ci = torch.empty(lnnz + 2, dtype=torch.int32, device="cuda")
+        va = torch.zeros(lnnz + 2, dtype=torch.float64, device="cuda")
+        B.check(L.b200_gen_stencil5_csr(n, off, nl, 5.0, -1.0, dp(rp), dp(ci), dp(va), None), "gen")
+        xl = torch.from_numpy(xh[off:off + nl].copy()).cuda()
+        hp = torch.from_numpy(xh[off - n:off].copy()).cuda() if g > 0 else None
+        hn = torch.from_numpy(xh[off + nl:off + nl + n].copy()).cuda() if g < P - 1 else None
+        y = torch.full((nl,), float("nan"), dtype=torch.float64, device="cuda")
+        band = B.Band(rp.data_ptr(), ci.data_ptr(), va.data_ptr(), lnnz + 2, off, nl, n, 0, hp.data_ptr() if hp is not None else None,
+                      hn.data_ptr() if hn is not None else None, None, None, 0, R, variant)
+        B.check(L.b200_stencil5_spmv(C.byref(band), dp(xl), dp(y), None), "spmv")
+        torch.cuda.synchronize()
+        if not np.array_equal(y.cpu().numpy(), y_full[off:off + nl]):
+            return "stencil n=%d P=%d g=%d variant=%d R=%d" % (n, P, g, variant, R)
+    return None
+
+
+def cg_case(L, rng):
+    n = int(rng.integers(2, 360))
+    N = n * n
+    mi = int(rng.choice([1, 2, 3, 7, 1000]))
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    rp64, oci, ova = orc.stencil5_csr_direct(n)
+    xo, ro, _ = orc.cg_device(rp64.astype(np.int32), oci, ova, n, 1, b, x0, mi, 1e-6)
+    hm = B.HostMatrix.synthetic_stencil(n)
+    opname = [b"stencil5-csr", b"stencil5-ellpack", b"cusparse-csr", b"ellpack"][int(rng.integers(0, 4))]
+    for sched in (0, 1):
+        L.b200_cg_set_schedule(sched)
+        op = L.get_operator(opname)
+        if op.contents.init(hm.ptr()) != 0:
+            return "cg init n=%d" % n
+        x = x0.copy()
+        st = B.CGStats()
+        rc = L.cg_solve_device(op, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(mi, 1e-6, 0, 0), C.byref(st))
+        op.contents.free()
+        L.b200_cg_set_schedule(1)
+        if rc != 0 or st.iterations != ro["iterations"] or np.linalg.norm(x - xo) > 1e-9 * np.linalg.norm(xo):
+            return "cg n=%d op=%s max_iters=%d sched=%d rc=%d it=%d/%d" % (n, opname.decode(), mi, sched, rc, st.iterations, ro["iterations"])
+    return None
+
+
+def csr_case(L, rng):
+    rows = int(rng.integers(1, 40000))
+    cols = int(rng.integers(max(1, rows // 2), rows * 2 + 2))
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        lens = rng.integers(0, 9, rows)
+    elif kind == 1:
+        lens = np.where(rng.random(rows) < 0.02, rng.integers(40, 700, rows), rng.integers(0, 6, rows))
+    elif kind == 2:
+        lens = np.full(rows, int(rng.integers(1, 30)))
+    else:
+        lens = rng.integers(10, 60, rows)
+    lens = np.minimum(lens, cols)
+    rp = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=rp[1:])
+    nnz = int(rp[-1])
+    if nnz == 0 or nnz > 3_000_000:
+        return None
+    ci = np.empty(nnz, dtype=np.int32)
+    for r in range(rows):  # sorted distinct columns per row
+        if lens[r]:
+            ci[rp[r]:rp[r + 1]] = np.sort(rng.choice(cols, size=int(lens[r]), replace=False))
+    va = rng.uniform(-1, 1, nnz)
+    xh = rng.standard_normal(cols)
+    orp = rp.astype(np.int32)
+    yo = orc.csr_spmv(orp, ci, va, xh)
+    variant = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 100]))
+    trp, tci, tva = (torch.from_numpy(a).cuda() for a in (orp, ci, va))
+    x = torch.from_numpy(xh).cuda()
+    y = torch.full((rows,), float("nan"), dtype=torch.float64, device="cuda")
+    plan = B.CsrPlan()
+    B.check(L.b200_csr_plan_build(dp(trp), rows, nnz, C.byref(plan), None), "plan")
+    plan.variant = variant
+    B.check(L.b200_spmv_csr(C.byref(plan), dp(trp), dp(tci), dp(tva), dp(x), dp(y), rows, 1.0, 0.0, None), "csr")
+    torch.cuda.synchronize()
+    yd = y.cpu().numpy()
+    scale = np.linalg.norm(yo) + 1e-300
+    if not np.all(np.isfinite(yd)) or np.linalg.norm(yd - yo) / scale > 1e-12:
+        return "csr rows=%d cols=%d kind=%d variant=%d err=%g" % (rows, cols, kind, variant, np.linalg.norm(yd - yo) / scale)
+    # lane-per-row (bit-exact) is guaranteed for groups of at most 256 entries = rows of at most 8 (smallest
+    # ring among the variants); longer rows may go warp-per-row (1e-12, checked above)
+    if kind in (0, 2) and lens.max() <= 8 and not np.array_equal(yd, yo):
+        return "csr not bit-exact rows=%d kind=%d variant=%d" % (rows, kind, variant)
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=90)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    L = B.load()
+    rng = np.random.default_rng(a.seed)
+    cases = [stencil_case, cg_case, csr_case]
+    counts, fails = [0, 0, 0], []
+    t0 = time.time()
+    while time.time() - t0 < a.seconds:
+        k = int(rng.integers(0, 3))
+        try:
+            msg = cases[k](L, rng)
+        except Exception as e:  # a CUDA error is sticky: report and stop
+            fails.append("%s raised %r" % (cases[k].__name__, e))
+            print(fails[-1], flush=True)
+            break
+        counts[k] += 1
+        if msg:
+            fails.append(msg)
+            print("FAIL", msg, flush=True)
+    print("stress: %d stencil, %d cg, %d csr cases, %d failures" % (counts[0], counts[1], counts[2], len(fails)))
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
