@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Randomised parity stress (development tool, complements tests/): random grid sizes, bands, tuning
+"""Randomised parity stress (run by hand on a GPU box; not collected by pytest, complements test_gpu_*.py): random grid sizes, bands, tuning
 variants, row-length mixes and CG schedules against the CPU oracle, through the C ABI.
 
-  python tools/stress.py [--seconds 90] [--seed 0]
+  python tests/stress_parity.py [--seconds 90] [--seed 0]     (lives under tests/: it uses the oracle as the checker)
 Prints one line per failing case and a summary; exit code 1 if anything failed."""
 import argparse
 import ctypes as C
