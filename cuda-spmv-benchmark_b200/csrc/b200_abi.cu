@@ -382,17 +382,21 @@ extern "C" int b200_csr_plan_build(const int* d_row_ptr, long long n_rows, long 
     plan->max_row_len = h[33];
     plan->mean_row_len = n_rows > 0 ? (double)nnz / (double)n_rows : 0.0;
     // Scheme pick from the histogram.  Every 32-row group decides at run time between lane-per-row
-    // (bit-exact k order, x gathered one group ahead) and warp-per-row; the histogram sets the row
-    // length above which a group goes warp-per-row: matrices whose MEDIAN row is longer than 16
-    // entries (bin 5 and up) switch early, because lane-per-row walks entries past its 8-deep x
-    // prefetch serially, while for short-row matrices an occasional 17..32-entry row is cheaper to
-    // finish in place than to hand the whole group to the warp-per-row path.
+    // (bit-exact k order, x gathered one group ahead) and warp-per-row; the histogram picks the ring:
+    //   * median row <= 8 entries: the small ring (variant 0, 4 x 128 entries, 32 warps/SM) -- a group
+    //     of 32 such rows fits it, everything runs lane-per-row at full occupancy;
+    //   * median row 9..32 entries: the large ring (variant 6, 8 x 128 entries, 16 warps/SM): groups of
+    //     up to 768 entries (24 per row) still run lane-per-row instead of falling to warp-per-row,
+    //     where 9..15-entry rows would leave most lanes idle;
+    //   * longer rows: warp-per-row throughout, small ring.
+    // Rows longer than vector_threshold (32 = the ring's wrap mirror) always go warp-per-row.
     unsigned long long acc = 0, half = (unsigned long long)(0.5 * (double)n_rows);
     int median_bin = 0;
     for (int b = 0; b < 33; b++) { acc += h[b]; if (acc >= half) { median_bin = b; break; } }
+    plan->variant = (median_bin == 4 || median_bin == 5) ? 6 : 0;
     plan->rows_per_block = 32 * kCsrGroupsPerItem;
-    plan->window = kCsrVariants[0].win;
-    plan->vector_threshold = (median_bin >= 5) ? 16 : 32;
+    plan->window = kCsrVariants[plan->variant].win;
+    plan->vector_threshold = 32;
     return B200_OK;
 }
 
@@ -456,7 +460,9 @@ extern "C" int b200_spmv_ellpack(const int* d_indices, const double* d_values, c
     a.row_ptr = nullptr; a.col_idx = d_indices; a.values = d_values; a.x = d_x; a.y = d_y;
     a.n_rows = n_rows; a.ell_width = width; a.vector_threshold = 1 << 20;  // ELLPACK rows are uniform: always stream
     a.alpha = alpha; a.beta = beta;
-    return launch_csr(a, 0, (cudaStream_t)stream);
+    // widths 9..24: the large ring keeps the rows lane-per-row (see b200_csr_plan_build)
+    const int variant = (csr_default_variant() == 0 && width > 8 && width <= 24) ? 6 : 0;
+    return launch_csr(a, variant, (cudaStream_t)stream);
 }
 
 extern "C" int b200_spmv_stencil5_ellpack(const double* d_values, const int* d_col_indices, const double* d_x,

@@ -331,6 +331,43 @@ def test_generic_csr_many_groups_per_warp(B, orc, torch_cuda, variant, shift):
     assert np.array_equal(y.cpu().numpy(), yo)
 
 
+@pytest.mark.parametrize("rowlen", [5, 12, 20, 40])
+def test_csr_plan_picks_ring_by_row_length_histogram(B, orc, torch_cuda, rowlen):
+    """the plan's histogram picks the ring: median row <= 8 -> small ring (variant 0), 9..32 -> large
+    ring (variant 6) so that such rows stay lane-per-row = bit-exact; longer -> warp-per-row (1e-12)"""
+    torch = torch_cuda
+    L = B.load()
+    rng = np.random.default_rng(rowlen)
+    rows = cols = 5000
+    lens = np.full(rows, rowlen)
+    ent = random_csr(rng, rows, cols, lens)
+    orp, oci, ova = orc.build_csr(rows, cols, ent.astype(orc.ENTRY_DTYPE))
+    xh = rng.standard_normal(cols)
+    yo = orc.csr_spmv(orp, oci, ova, xh)
+    rp, ci, va = (torch.from_numpy(a).cuda() for a in (orp, oci, ova))
+    x = torch.from_numpy(xh).cuda()
+    y = torch.full((rows,), float("nan"), dtype=torch.float64, device="cuda")
+    plan = B.CsrPlan()
+    B.check(L.b200_csr_plan_build(dptr(rp), rows, len(ova), C.byref(plan), None), "plan")
+    assert plan.variant == (6 if 8 < rowlen <= 32 else 0)
+    B.check(L.b200_spmv_csr(C.byref(plan), dptr(rp), dptr(ci), dptr(va), dptr(x), dptr(y), rows, 1.0, 0.0, None), "csr")
+    torch.cuda.synchronize()
+    yd = y.cpu().numpy()
+    if rowlen <= 24:
+        assert np.array_equal(yd, yo)
+    else:
+        assert np.linalg.norm(yd - yo) / np.linalg.norm(yo) < 1e-12
+    w, oidx, oval = orc.build_ellpack(orp, oci, ova, rows, cols)
+    idx, val = torch.from_numpy(oidx).cuda(), torch.from_numpy(oval).cuda()
+    y.fill_(float("nan"))
+    B.check(L.b200_spmv_ellpack(dptr(idx), dptr(val), dptr(x), dptr(y), rows, w, 1.0, 0.0, None), "ell")
+    torch.cuda.synchronize()
+    if rowlen <= 24:
+        assert np.array_equal(y.cpu().numpy(), yo)
+    else:
+        assert np.linalg.norm(y.cpu().numpy() - yo) / np.linalg.norm(yo) < 1e-12
+
+
 @pytest.mark.parametrize("fmt", ["csr", "ell"])
 @pytest.mark.parametrize("n", [7, 130, 900])
 def test_generic_spmv_with_fused_dot(B, orc, torch_cuda, fmt, n):
