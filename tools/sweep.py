@@ -126,6 +126,8 @@ def main():
         rec("cg_update_xr(K2)", ms, best, 48.0 * N)
         ms, best = timeit(lambda: B.check(L.b200_cg_update_p(N, dptr(sc), dptr(r), dptr(p), s), "k3"))
         rec("cg_update_p(K3)", ms, best, 24.0 * N)
+        ms, best = timeit(lambda: B.check(L.b200_cg_update_r(N, dptr(sc), dptr(Ap), dptr(r), dptr(partials), C.byref(npart), s), "k2r"))
+        rec("cg_update_r(K2r)", ms, best, 24.0 * N)
         ms, best = timeit(lambda: B.check(L.b200_cg_reduce(dptr(partials), 1184, 3, 3, 1e-6, None, None, dptr(sc),
                                                            0, 1, 1, None, None, s), "red"))
         rec("cg_reduce(1184 partials)", ms, best, 1184 * 8.0)
