@@ -133,6 +133,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank unless the caller set it; the CPU arm runs on
+    # rank 0 alone and is meant to use all host cores
+    if os.environ.get("OMP_NUM_THREADS") == "1" and ("TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     vals = []
     for s in range(args.warmup + args.steps):
         v, threads, sample = cpu_cg_sample(args.grid, args.cpu_grid)
@@ -239,7 +243,13 @@ def run_b200(args):
     n = args.grid
     N = n * n
     dist = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner straight to fd 1 when the communicator comes up: keep stdout for
+        # the one JSON line, send everything else to stderr until then
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         import mgpu_bootstrap
@@ -399,8 +409,12 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, threads, sample = cpu_cg_sample(n, args.cpu_grid)
         line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": threads, "kind": "port", "sample": sample}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         L.b200_mgpu_finalize()
