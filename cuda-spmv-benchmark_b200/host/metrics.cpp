@@ -195,7 +195,7 @@ extern "C" int get_gpu_properties(BenchmarkMetrics* m) {
     cudaDeviceProp prop;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaGetDeviceProperties(&prop, dev));
-    snprintf(m->gpu_info.name, sizeof m->gpu_info.name, "%s", prop.name);
+    snprintf(m->gpu_info.name, sizeof m->gpu_info.name, "%.*s", (int)sizeof m->gpu_info.name - 1, prop.name);
     m->gpu_info.memory_mb = (int)(prop.totalGlobalMem / (1024 * 1024));
     snprintf(m->gpu_info.compute_capability, sizeof m->gpu_info.compute_capability, "%d.%d", prop.major, prop.minor);
     m->gpu_info.multiprocessor_count = prop.multiProcessorCount;
