@@ -183,3 +183,23 @@ def test_mpirun_shim_maps_ranks_to_gpus():
     r = run("-np", "1", "./bin/cg_solver", "m.mtx", "--mode=stencil5-csr")
     assert r.stdout.strip() == "./bin/cg_solver m.mtx --mode=stencil5-csr"
     assert run("-np", "4").returncode == 2
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (CPU arm, runs anywhere): one JSON line with the contract's keys"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-grid", "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["value"] > 0 and line["config"]["workload"].startswith("cg_20000x20000")

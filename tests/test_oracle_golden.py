@@ -233,3 +233,48 @@ def test_oracle_matches_reference_gpu_outputs(orc, tmp_path):
                 assert math.isclose(res["residual_norm"], c["residual_norm"], rel_tol=1e-9), (n, opname)
                 assert math.isclose(res["solution_sum"], c["solution_sum"], rel_tol=1e-12), (n, opname)
                 assert math.isclose(res["solution_norm"], c["solution_norm"], rel_tol=1e-12), (n, opname)
+
+
+def test_pcg_restatement_vs_independent_numpy_and_scipy(orc):
+    """orc_pcg_device has no reference counterpart (the reference ships no preconditioner): pin it
+    against an independent numpy statement of Jacobi-PCG with the reference's stopping rule, and
+    against scipy's cg with the same preconditioner for the solution itself."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    n = 60
+    N = n * n
+    rng = np.random.default_rng(3)
+    ent = orc.stencil5_entries(n, 5.0, -1.0)
+    diag = ent["row"] == ent["col"]
+    ent["value"][diag] = 4.0 + rng.uniform(0.0, 50.0, int(diag.sum()))
+    rp, ci, va = orc.build_csr(N, N, ent)
+    A = sp.csr_matrix((va, ci, rp), shape=(N, N))
+    b = rng.standard_normal(N)
+    x, res = orc.pcg_device(rp, ci, va, n, 0, b, np.zeros(N), 1000, 1e-8)
+    # independent restatement
+    dinv = 1.0 / A.diagonal()
+    xr = np.zeros(N)
+    r = b - A @ xr
+    z = dinv * r
+    p = z.copy()
+    rho = r @ z
+    r0 = math.sqrt(r @ r)
+    it = 0
+    for it in range(1, 1001):
+        Ap = A @ p
+        alpha = rho / (p @ Ap)
+        xr += alpha * p
+        r -= alpha * Ap
+        if math.sqrt(r @ r) / r0 < 1e-8:
+            break
+        z = dinv * r
+        rho_new = r @ z
+        p = z + (rho_new / rho) * p
+        rho = rho_new
+    assert res["converged"] == 1 and res["iterations"] == it
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-10
+    xs, info = spl.cg(A, b, rtol=1e-12, atol=0.0, M=sp.diags(dinv))
+    assert info == 0 and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-7
+    # and it beats plain CG on this matrix
+    _, rc, _ = orc.cg_device(rp, ci, va, n, 0, b, np.zeros(N), 1000, 1e-8)
+    assert res["iterations"] < rc["iterations"]
