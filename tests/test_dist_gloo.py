@@ -81,7 +81,7 @@ def test_bootstrap_world2_gloo(world, n):
 def test_partition_rule_matches_oracle():
     import mgpu_bootstrap as mb
     import orc
-    for N in (81 * 81, 20000 * 20000, 17):
+    for N in (81 * 81, 20000 * 20000, 17, 56576 * 56576):  # the last one: 3.2e9 rows, beyond 32 bits
         for P in (1, 2, 3, 4, 8):
             cover = 0
             for r in range(P):

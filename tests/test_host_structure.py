@@ -203,3 +203,23 @@ def test_bench_reference_arm_json_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["value"] > 0 and line["config"]["workload"].startswith("cg_20000x20000")
+
+
+def test_synthetic_matrix_beyond_32_bit_rows(B):
+    """the synthetic stencil is defined by grid_size; the reference's 32-bit rows / cols / nnz fields
+    saturate instead of wrapping (weak scaling: 56576^2 = 3.2e9 rows over 8 GPUs), and the closed-form
+    non-zero prefix stays exact in 64 bits"""
+    L = B.load()
+    m = L.b200_synthetic_stencil(56576)
+    assert m.grid_size == 56576 and m.rows == 2**31 - 1 and m.cols == 2**31 - 1 and m.nnz == 2**31 - 1
+    assert not m.entries
+    m = L.b200_synthetic_stencil(20000)
+    assert m.rows == 400_000_000 and m.nnz == 1_999_920_000
+    n = 56576
+    N = n * n
+    assert L.b200_stencil5_nnz_before(N, n) == 5 * N - 4 * n
+    assert L.b200_stencil5_nnz_before(n, n) == 4 * n - 2  # first grid row: two corners of 3, n - 2 rows of 4
+    # per-band non-zeros of the 8-GPU weak-scaling case stay below 2^31 (32-bit local offsets)
+    for r in range(8):
+        lo, hi = r * (N // 8), (r + 1) * (N // 8)
+        assert 0 < L.b200_stencil5_nnz_before(hi, n) - L.b200_stencil5_nnz_before(lo, n) < 2**31
