@@ -151,11 +151,12 @@ __global__ void __launch_bounds__(WARPS * 32) csr_warp_stream_kernel(const CsrAr
 //     mbarrier complete_tx, L2 evict-first): independent of where rows begin, no registers tied
 //     up, up to STAGES-1 windows in flight per warp.  Row extents are coalesced 4-byte cp.async
 //     loads into a small shared-memory queue, issued three pipeline turns before they are needed.
-//   * Short rows ("lane per row", groups with at most RING/2 - WIN entries and rows no longer than
-//     `vector_threshold`): every lane owns one row of the group.  One group AHEAD of the
+//   * Short rows ("lane per row", groups with at most RING - 2 WIN entries and rows no longer than
+//     `vector_threshold` <= 32): every lane owns one row of the group.  One group AHEAD of the
 //     arithmetic it reads its first 8 column ids from shared memory and launches the x gathers
 //     into registers, so the gather latency hides behind the previous group's work; then
-//     sum = fma(v[k], x[col[k]], sum) for k ascending -- bit-identical to the scalar reference.
+//     sum = fma(v[k], x[col[k]], sum) for k ascending -- bit-identical to the scalar reference
+//     (entries past the 8th of a row are gathered in place).
 //   * Long rows ("warp per row"): lanes stride over the row, lane l takes the entries with
 //     (k - row_start) % 32 == l in k order, butterfly sum at the row end (rounding-level
 //     difference to the sequential order, documented tolerance 1e-12).  Rows may be longer than
