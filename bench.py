@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--weak", action="store_true",
                     help="weak scaling (BASELINE configs[4]): 20k x 20k rows PER GPU, square grid of side "
                          "20000*sqrt(N) rounded to a multiple of 2N (bands stay grid-row aligned); not the headline metric")
-    ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--cpu-grid", type=int, default=0,
+                    help="CPU arm: run (and report) this grid instead of --grid (0 = --grid, reduced only if host RAM is short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operators", action="store_true", help="skip the 10k x 10k operator comparison (configs[1])")
     return ap.parse_args()
@@ -103,30 +104,72 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference has no CPU compute path -- BASELINE.md section 3)
 # ------------------------------------------------------------------------------------------------
-def cpu_cg_sample(grid_full, cpu_grid, repeats=1):
-    """Bounded sample: full CG to convergence on a smaller grid with the OpenMP oracle, scaled to
-    the full workload by rows x iterations (streaming kernels: time/row/iteration is size independent)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import orc
-    threads = orc.num_threads()
-    n = cpu_grid or (6000 if threads >= 16 else 4000 if threads >= 8 else 2500)
-    rp64, ci, va = orc.stencil5_csr_direct(n)
-    rp = rp64.astype(np.int32)
-    b, x0 = np.ones(n * n), np.zeros(n * n)
-    best, iters = None, None
-    for _ in range(repeats):
+KAT_20K = {"iterations": 14, "residual_norm": 1.08428e-2, "solution_sum": 3.9995055965e8, "solution_norm": 1.9997869532e4}
+KAT_10K = {"iterations": 14, "solution_sum": 9.9975281007e7, "solution_norm": 9.9978695581e3}
+
+
+def mem_available_bytes():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    return None
+
+
+class CpuCG:
+    """The CPU arm: full CG to convergence (b = 1, x0 = 0, tol 1e-6) with the OpenMP oracle port of
+    cg_solve_device on the CSR stencil operator, on the grid it is asked for.  Nothing is scaled or
+    extrapolated: the grid that runs is the grid that is reported.  If the host cannot hold the
+    matrix (112 B/row: CSR 64 + five vectors 40 + conversion slack) the grid is reduced and the
+    reduced grid is what `config` names."""
+    BYTES_PER_ROW = 112.0
+
+    def __init__(self, grid, forced_grid=0):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import orc
+        self.np, self.orc = np, orc
+        self.threads = orc.num_threads()
+        self.requested = grid
+        n = forced_grid or grid
+        avail = mem_available_bytes()
+        self.reduced = None
+        if not forced_grid and avail is not None and self.BYTES_PER_ROW * n * n > 0.85 * avail:
+            n = int((0.85 * avail / self.BYTES_PER_ROW) ** 0.5) // 1000 * 1000
+            self.reduced = "host has %.0f GB available, %dx%d needs %.0f GB" % (avail / 1e9, grid, grid,
+                                                                                 self.BYTES_PER_ROW * grid * grid / 1e9)
+        self.n = max(n, 3)
         t0 = time.perf_counter()
-        x, res, _ = orc.cg_device(rp, ci, va, n, 1, b, x0, MAX_ITERS, TOL)
-        dt = (time.perf_counter() - t0) * 1e3
-        best = dt if best is None else min(best, dt)
-        iters = res["iterations"]
-    full_iters = 14  # 20k^2 (BASELINE.md); every size >= 10k converges in 14
-    scaled = best * (grid_full * grid_full * full_iters) / (n * n * iters)
-    sample = ("full CG (oracle port of cg_solve_device, CSR stencil operator, OpenMP %d threads) on a %dx%d grid "
-              "(%d rows, %d iterations, %.0f ms), scaled by rows*iterations to %dx%d / %d iterations"
-              % (threads, n, n, n * n, iters, best, grid_full, grid_full, full_iters))
-    return scaled, threads, sample
+        rp64, self.ci, self.va = orc.stencil5_csr_direct(self.n)
+        self.rp = rp64.astype(np.int32)
+        del rp64
+        self.b = np.ones(self.n * self.n)
+        self.setup_s = time.perf_counter() - t0
+        self.last = None
+
+    def solve(self):
+        """one full solve -> ms"""
+        x0 = self.np.zeros(self.n * self.n)
+        t0 = time.perf_counter()
+        _, res, _ = self.orc.cg_device(self.rp, self.ci, self.va, self.n, 1, self.b, x0, MAX_ITERS, TOL, hist=0, inplace=True)
+        ms = (time.perf_counter() - t0) * 1e3
+        self.last = res
+        if not res["converged"]:
+            raise SystemExit("CPU arm: CG did not converge")
+        return ms
+
+    def workload(self):
+        return "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (self.n, self.n)
+
+    def sample(self, solves, ms):
+        s = ("full CG to convergence (oracle port of cg_solve_device, stencil5-csr operator, OpenMP %d threads) on the %dx%d grid "
+             "(%d rows, %d iterations, %d timed solve(s), %.0f ms each; matrix build %.1f s untimed); measured, not scaled"
+             % (self.threads, self.n, self.n, self.n * self.n, self.last["iterations"], solves, ms, self.setup_s))
+        if self.n != self.requested:
+            s += "; REDUCED from %dx%d: %s" % (self.requested, self.requested, self.reduced or "--cpu-grid")
+        return s
 
 
 def run_reference(args):
@@ -137,18 +180,21 @@ def run_reference(args):
     # rank 0 alone and is meant to use all host cores
     if os.environ.get("OMP_NUM_THREADS") == "1" and ("TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ):
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    vals = []
-    for s in range(args.warmup + args.steps):
-        v, threads, sample = cpu_cg_sample(args.grid, args.cpu_grid)
-        if s >= args.warmup:
-            vals.append(v)
+    cpu = CpuCG(args.grid, args.cpu_grid)
+    for _ in range(args.warmup):
+        cpu.solve()
+    vals = [cpu.solve() for _ in range(args.steps)]
     val = sum(vals) / len(vals)
+    n = cpu.n
     line = {"metric": METRIC, "value": val, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": val, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (args.grid, args.grid), "grid": args.grid,
-                       "rows": args.grid ** 2, "tol": TOL},
-            "cpu_baseline": {"value": val, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": cpu.workload(), "grid": n, "rows": n * n, "nnz": 5 * n * n - 4 * n, "tol": TOL,
+                       "iterations": cpu.last["iterations"], "operator": "stencil5-csr (oracle port)",
+                       "requested_grid": args.grid, "host_threads": cpu.threads},
+            "cg": {k: cpu.last[k] for k in ("iterations", "residual_norm", "solution_sum", "solution_norm")},
+            "cpu_baseline": {"value": val, "unit": "ms", "cores": cpu.threads, "kind": "port",
+                             "sample": cpu.sample(len(vals), val)},
             "e2e": {"value": val, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -407,8 +453,11 @@ def run_b200(args):
         torch.cuda.empty_cache()
         line["operators_10k"] = operator_table(L, B, torch, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, threads, sample = cpu_cg_sample(n, args.cpu_grid)
-        line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": threads, "kind": "port", "sample": sample}
+        del b_host, x_host  # 6.4 GB of pinned host memory the CPU arm can use
+        cpu = CpuCG(n, args.cpu_grid)
+        v = cpu.solve()
+        line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "grid": cpu.n,
+                                "workload": cpu.workload(), "sample": cpu.sample(1, v)}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

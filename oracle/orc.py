@@ -237,14 +237,16 @@ def dot_sequential(x, y):
     return float(lib().orc_dot_sequential(len(x), _p(x), _p(y)))
 
 
-def cg_device(rp, ci, va, grid, op, b, x0, max_iters=1000, tol=1e-6, hist=64):
-    """Restated cg_solve_device.  op: 0 generic CSR, 1 stencil5.  -> (x, result dict, rel history)"""
+def cg_device(rp, ci, va, grid, op, b, x0, max_iters=1000, tol=1e-6, hist=64, inplace=False):
+    """Restated cg_solve_device.  op: 0 generic CSR, 1 stencil5.  -> (x, result dict, rel history)
+    inplace: x0 (contiguous float64) is overwritten with the solution instead of being copied."""
     rows = len(rp) - 1
     c = _csr_struct(rp, ci, va, rows, rows)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    x = np.array(x0, dtype=np.float64, copy=True)
+    x = x0 if inplace else np.array(x0, dtype=np.float64, copy=True)
+    assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]
     res = CGResult()
-    h = np.zeros(hist, dtype=np.float64)
+    h = np.zeros(max(hist, 1), dtype=np.float64)
     rc = lib().orc_cg_device(C.byref(c), grid, op, _p(b), _p(x), max_iters, tol, C.byref(res), _p(h), hist)
     if rc:
         raise RuntimeError("orc_cg_device rc=%d" % rc)

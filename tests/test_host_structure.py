@@ -202,7 +202,14 @@ def test_bench_reference_arm_json_contract():
     assert line["impl"] == "reference" and line["unit"] == "ms" and line["higher_is_better"] is False
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["value"] > 0 and line["config"]["workload"].startswith("cg_20000x20000")
+    # the arm reports the grid it actually ran -- never a scaled number under the 20k label
+    assert line["value"] > 0 and line["config"]["workload"].startswith("cg_200x200_")
+    assert line["config"]["grid"] == 200 and line["config"]["rows"] == 40000
+    assert line["config"]["requested_grid"] == 20000
+    assert "REDUCED from 20000x20000" in line["cpu_baseline"]["sample"]
+    assert "scaled" not in line["cpu_baseline"]["sample"].replace("not scaled", "")
+    # the oracle's own KAT for this grid (tests/test_oracle_golden.py pins the oracle itself)
+    assert line["cg"]["iterations"] == line["config"]["iterations"] > 0
 
 
 def test_synthetic_matrix_beyond_32_bit_rows(B):
