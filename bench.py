@@ -48,6 +48,13 @@ def parse():
                     help="CPU arm: run (and report) this grid instead of --grid (0 = --grid, reduced only if host RAM is short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operators", action="store_true", help="skip the 10k x 10k operator comparison (configs[1])")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N > 1 without torchrun: ONE process drives all N GPUs (one enqueue thread per GPU), the "
+                         "north-star topology / the reference CLI's `cg_solver_mgpu_stencil`")
+    ap.add_argument("--timers-every", type=int, default=4,
+                    help="record the per-phase CUDA events (roofline.avg_launch_ms) on every K-th timed step only: an event "
+                         "between two kernels keeps the second one from being scheduled under the tail of the first "
+                         "(programmatic dependent launch); 1 = every step")
     return ap.parse_args()
 
 
@@ -268,12 +275,13 @@ def run_b200(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    single = args.single_process and args.gpus > 1
+    world = args.gpus if single else int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
+    if world != args.gpus and not single:
         if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU)" % args.gpus)
+            raise SystemExit("bench.py: --gpus %d needs torchrun (one process per GPU) or --single-process" % args.gpus)
     torch.cuda.set_device(local_rank)
     L = B.load()
     if args.weak:
@@ -290,7 +298,11 @@ def run_b200(args):
     N = n * n
     dist = None
     saved_stdout = None
-    if world > 1:
+    if single:
+        devs = (C.c_int * world)(*range(world))
+        if L.b200_mgpu_init_single_process(world, devs, n) != 0:
+            raise SystemExit("b200_mgpu_init_single_process failed")
+    elif world > 1:
         # NCCL prints its version banner straight to fd 1 when the communicator comes up: keep stdout for
         # the one JSON line, send everything else to stderr until then
         sys.stdout.flush()
@@ -303,6 +315,10 @@ def run_b200(args):
         dist.barrier()
 
     def barrier():
+        if single:
+            for d in range(world):
+                torch.cuda.synchronize(d)
+            return
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -310,13 +326,14 @@ def run_b200(args):
 
     mat = B.HostMatrix.synthetic_stencil(n)
     import mgpu_bootstrap
-    nl, off = mgpu_bootstrap.partition(N, world, rank)
+    nl, off = (N, 0) if single else mgpu_bootstrap.partition(N, world, rank)
     # pinned host buffers of the local slice; the solver only touches [off, off+nl) of b and x
     b_host = torch.ones(nl, dtype=torch.float64).pin_memory()
     x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
     b_ptr = b_host.data_ptr() - off * 8
     x_ptr = x_host.data_ptr() - off * 8
-    cfg = B.cg_config(MAX_ITERS, TOL, 0, 1)  # detailed timers: event records only, no extra syncs
+    cfg_timed = B.cg_config(MAX_ITERS, TOL, 0, 1)  # detailed timers: event records only, no extra syncs
+    cfg_plain = B.cg_config(MAX_ITERS, TOL, 0, 0)
 
     if world == 1:
         op = L.get_operator(b"stencil5-csr")
@@ -324,18 +341,18 @@ def run_b200(args):
             raise SystemExit("operator init failed")
         stats = B.CGStats()
 
-        def solve():
+        def solve(cfg):
             return L.cg_solve_device(op, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
     else:
         stats = B.CGStatsMultiGPU()
 
-        def solve():
+        def solve(cfg):
             return L.cg_solve_mgpu_partitioned(None, mat.ptr(), b_ptr, x_ptr, cfg, C.byref(stats))
 
     for _ in range(args.warmup):
         x_host.zero_()
         barrier()
-        if solve() != 0:
+        if solve(cfg_timed) != 0:
             raise SystemExit("warm-up solve failed")
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -344,15 +361,26 @@ def run_b200(args):
     dev_ms, wall_ms, k1_ms, k1_cnt, iters = [], [], 0.0, 0, None
     ph = (C.c_double * 9)()
     pc = (C.c_int * 9)()
+    tl = (C.c_double * 8)()
+    tc = (C.c_int * 8)()
+    gp = (C.c_double * 8)()
+    gap_ms, steps_without_events = [0.0] * 8, 0
     barrier()
     t_block0 = time.perf_counter()
     phase_sum = [0.0] * 9
-    for _ in range(args.steps):
+    tail_ms, tail_n, steps_with_events = [0.0] * 8, [0] * 8, 0
+    kats = []
+    for step in range(args.steps):
         x_host.zero_()  # initial guess x0 = 0 (not part of the solve)
         barrier()
+        with_events = (step % max(args.timers_every, 1) == 0)
         t0 = time.perf_counter()
-        rc = solve()
-        torch.cuda.synchronize()
+        rc = solve(cfg_timed if with_events else cfg_plain)
+        if single:
+            for d in range(world):
+                torch.cuda.synchronize(d)
+        else:
+            torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         if rc != 0:
             raise SystemExit("solve failed rc=%d" % rc)
@@ -363,21 +391,47 @@ def run_b200(args):
             d, wall = float(t[0]), float(t[1])
         dev_ms.append(d)
         wall_ms.append(wall)
-        L.b200_last_phase_times(ph, pc)
-        k1_ms += ph[1]
-        k1_cnt += pc[1]
-        for t in range(9):
-            phase_sum[t] += ph[t] / args.steps
+        if with_events:
+            L.b200_last_phase_times(ph, pc)
+            k1_ms += ph[1]
+            k1_cnt += pc[1]
+            steps_with_events += 1
+            for t in range(9):
+                phase_sum[t] += ph[t]
+        L.b200_last_tail_times(tl, tc)
+        L.b200_last_gap_times(gp)
+        for t in range(8):
+            tail_ms[t] += tl[t]
+            tail_n[t] += tc[t]
+            if not with_events:
+                gap_ms[t] += gp[t]
+        steps_without_events += 0 if with_events else 1
         iters = stats.iterations
         if not stats.converged:
             raise SystemExit("CG did not converge")
+        kats.append((stats.iterations, stats.residual_norm, stats.solution_sum, stats.solution_norm))
     barrier()
     block_ms = (time.perf_counter() - t_block0) * 1e3
     launches = L.b200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    phase_sum = [v / max(steps_with_events, 1) for v in phase_sum]
+    # parity gate inside the bench: the timed solves must reproduce the known answers of this grid
+    #  on any number of GPUs, bit-identically from step to step
+    kat = {20000: KAT_20K, 10000: KAT_10K}.get(n) if not args.weak else None
+    if len(set(kats)) != 1:
+        raise SystemExit("bench.py: timed solves are not bit-reproducible: %r" % sorted(set(kats)))
+    if kat is not None:
+        import math
+        it_k, res_k, sum_k, norm_k = kats[0]
+        bad = [k for k, got, tol in (("iterations", it_k, 0), ("solution_sum", sum_k, 1e-10), ("solution_norm", norm_k, 1e-10),
+                                     ("residual_norm", res_k, 1e-5))
+               if k in kat and not (got == kat[k] if tol == 0 else math.isclose(got, kat[k], rel_tol=tol))]
+        if bad:
+            raise SystemExit("bench.py: known-answer mismatch on %s: got %r, expected %r" % (bad, kats[0], kat))
 
     ms = sum(dev_ms) / len(dev_ms)
     e2e_ms = sum(wall_ms) / len(wall_ms)
+    world_div = world if single else 1  # rows per RANK behind nl
     peak, peak_src = measured_peak()
     rows_local = nl
     nnz_local = L.b200_stencil5_nnz_before(off + nl, n) - L.b200_stencil5_nnz_before(off, n)
@@ -418,7 +472,8 @@ def run_b200(args):
     line = {
         "metric": METRIC if not args.weak else "cg_solve_ms_weak_20k_x_20k_rows_per_gpu_stencil5_fp64",
         "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": False, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "ms_per_step": ms, "ms_steps": [round(v, 3) for v in dev_ms],
+        "higher_is_better": False, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic", "impl": "b200",
         "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (n, n), "grid": n, "rows": N,
@@ -428,6 +483,7 @@ def run_b200(args):
                    "cache": "vectors (3.2 GB each) and matrix (16 GB values) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 16 * nl, "d2h_bytes_per_step": 8 * nl,
                 "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
+                "pcie_gbs_per_rank": round(24.0 * nl / world_div / max((e2e_ms - ms) * 1e-3, 1e-9) / 1e9, 2),
                 "host_buffers": "pinned", "block_wall_ms_per_step": block_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved,
@@ -438,16 +494,42 @@ def run_b200(args):
         "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV launch inside CG (see roofline.kernel)"},
         "cg": {"iterations": iters, "residual_norm": stats.residual_norm, "solution_sum": stats.solution_sum,
                "solution_norm": stats.solution_norm,
-               "schedule": "deferred-x (4 launches, 112 B/row per iteration)" if deferred_x
-               else "classic (5 launches, 128 B/row per iteration)",
+               "schedule": "deferred-x (2 launches, 112 B/row per iteration)" if deferred_x
+               else "classic (3 launches, 128 B/row per iteration)",
+               "topology": ("one process, %d GPUs, one enqueue thread per GPU" % world) if single
+               else ("one process per GPU (torchrun), peer memory via CUDA IPC" if world > 1 else "one GPU"),
                "iter_bytes_model": iter_bytes, "solve_bytes_model": solve_bytes,
                "solve_gb_s": solve_bytes / (ms * 1e-3) / 1e9},
-        "phases_ms_per_step": dict(zip(["_", "spmv(K1/K1F)", "reduce_pAp", "update_r(K2r)" if deferred_x else "update_xr(K2)",
-                                        "reduce_rr", "finish_x" if deferred_x else "update_p(K3)",
-                                        "halo_dir" if deferred_x else "halo_push", "residual_init", "reduce_rr0"],
+        # per-phase CUDA-event times of the steps that recorded them (every --timers-every-th step); the final
+        # sums, scalar recurrences and rank exchanges run in the TAIL of the producing kernels (no reduce launches)
+        "phases_ms_per_step": dict(zip(["_", "spmv(K1/K1F incl. p.Ap tail)", "reduce_pAp(stand-alone)",
+                                        "update_r(K2r incl. r.r tail)" if deferred_x else "update_xr(K2 incl. r.r tail)",
+                                        "reduce_rr(stand-alone)", "finish_x" if deferred_x else "update_p(K3)",
+                                        "halo_dir(setup)" if deferred_x else "halo_push", "residual_init", "reduce_rr0"],
                                        [round(v, 4) for v in phase_sum])),
+        "phase_event_steps": steps_with_events,
+        # device-measured (globaltimer) duration of the reduction tails: fixed-order final sum + LL exchange over
+        # NVLink peer memory (includes waiting for the slowest rank) + scalar update, per exchange, rank 0
+        "tails_us_per_exchange": {nm: (round(1e3 * tail_ms[k] / tail_n[k], 3) if tail_n[k] else None)
+                                  for k, nm in ((0, "r0.r0"), (1, "p.Ap"), (2, "r.r"), (3, "checksum"))},
+        "tails_ms_per_step": round(sum(tail_ms[k] for k in (0, 1, 2)) / args.steps, 4),
+        # device-clock time between consecutive tails in the steps WITHOUT events (programmatic launches overlap
+        # there): spmv = halo direction + K1 / K1F + its reduce kernel's group sums, update_r = K2r / K2
+        "phases_device_clock_ms_per_step": {"steps": steps_without_events,
+                                            "spmv": round(gap_ms[1] / max(steps_without_events, 1), 4),
+                                            "update_r": round(gap_ms[2] / max(steps_without_events, 1), 4)},
         "clocks": clocks,
     }
+    if world > 1:
+        # the halo exchange on its own (it rides inside K2r during a solve): isolated push of one grid row to each
+        # neighbour, against NVLink 5's 900 GB/s per direction -- latency-bound by construction (160 KB per edge)
+        us, nb = C.c_double(), C.c_longlong()
+        if L.b200_mgpu_halo_probe(50, C.byref(us), C.byref(nb)) == 0 and us.value > 0:
+            line["halo"] = {"bytes_per_iter_per_direction": int(nb.value), "neighbours": 2,
+                            "us": round(us.value, 3), "gb_s_per_direction": round(nb.value / us.value / 1e3, 2),
+                            "frac_of_900GBs": round(nb.value / (us.value * 1e-6) / 900e9, 5),
+                            "how": "50 back-to-back b200_halo_push launches (peer stores + arrival word), CUDA events, slowest local rank; "
+                                   "inside a solve the same stores are issued by K2r and overlap its stream"}
     if world == 1 and not args.no_operators and not args.weak:
         op.contents.free()
         torch.cuda.empty_cache()
@@ -468,6 +550,8 @@ def run_b200(args):
         dist.barrier()
         L.b200_mgpu_finalize()
         dist.destroy_process_group()
+    elif single:
+        L.b200_mgpu_finalize()
     return 0
 
 

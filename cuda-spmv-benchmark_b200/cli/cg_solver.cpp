@@ -15,7 +15,8 @@ int main(int argc, char** argv) {
     for (auto& m : a.modes)
         if (!get_operator(m.c_str())) { fprintf(stderr, "Unknown mode '%s'\n", m.c_str()); return EXIT_FAILURE; }
     MatrixData mat;
-    if (load_or_generate(a, &mat)) return EXIT_FAILURE;
+    void* d_entries = nullptr;
+    if (load_or_generate(a, &mat, &d_entries)) return EXIT_FAILURE;
     printf("Matrix: %d x %d, %d nonzeros, grid %d\n", mat.rows, mat.cols, mat.nnz, mat.grid_size);
     std::vector<double> b((size_t)mat.rows, 1.0), x((size_t)mat.rows, 0.0);
     CGConfig cfg = {a.maxiter, a.tol, 1, a.timers ? 1 : 0};
@@ -27,7 +28,7 @@ int main(int argc, char** argv) {
             fprintf(stderr, "[ERROR] Operator '%s' does not support device-native interface\n", op->name);
             return EXIT_FAILURE;
         }
-        if (op->init(&mat) != 0) { fprintf(stderr, "Failed to initialize operator '%s'\n", op->name); return EXIT_FAILURE; }
+        if (init_operator(op, &mat, d_entries) != 0) { fprintf(stderr, "Failed to initialize operator '%s'\n", op->name); return EXIT_FAILURE; }
         CGStats st;
         CGConfig quiet = cfg;
         quiet.verbose = 0;
@@ -79,5 +80,6 @@ int main(int argc, char** argv) {
         op->free();
     }
     free(mat.entries);
+    if (d_entries) b200_free_device(d_entries);
     return EXIT_SUCCESS;
 }

@@ -1,7 +1,8 @@
-// cg_solver_mgpu_stencil <file.mtx | --grid=n> [--gpus=P] [--timers] [--json=F] [--csv=F]
+// cg_solver_mgpu_stencil <file.mtx | --grid=n> [--gpus=P] [--timers] [--json=F] [--csv=F] [--precond=jacobi]
 // reference src/main/cg_solver_mgpu_stencil.cu:22-197 (there: mpirun -np P, one rank per GPU).
 // Here one process drives P GPUs (default: all visible); max_iters 1000, tol 1e-6, 3 warm-ups,
 // cg_benchmark_with_stats_mgpu_partitioned(10), Sum(x)/Norm2(x) lines, export_cg_mgpu_json.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime_api.h>
 
 #include "cli_common.h"
@@ -31,13 +32,29 @@ int main(int argc, char** argv) {
     CGConfigMultiGPU quiet = cfg;
     quiet.verbose = 0;
     CGStatsMultiGPU st;
+    auto solve = a.jacobi ? pcg_solve_mgpu_partitioned : cg_solve_mgpu_partitioned;
     for (int w = 0; w < 3; w++) {
         std::fill(x.begin(), x.end(), 0.0);
-        if (cg_solve_mgpu_partitioned(nullptr, &mat, b.data(), x.data(), quiet, &st) != 0) { fprintf(stderr, "CG solve failed\n"); return EXIT_FAILURE; }
+        if (solve(nullptr, &mat, b.data(), x.data(), quiet, &st) != 0) { fprintf(stderr, "CG solve failed\n"); return EXIT_FAILURE; }
     }
+    // one solve inside the profiler window (reference src/main/cg_solver_mgpu_stencil.cu:115-117)
+    std::fill(x.begin(), x.end(), 0.0);
+    cudaProfilerStart();
+    if (solve(nullptr, &mat, b.data(), x.data(), quiet, &st) != 0) { fprintf(stderr, "CG solve failed\n"); return EXIT_FAILURE; }
+    cudaProfilerStop();
     std::fill(x.begin(), x.end(), 0.0);
     BenchmarkStats bs;
-    if (cg_benchmark_with_stats_mgpu_partitioned(nullptr, &mat, b.data(), x.data(), cfg, a.runs, &bs, &st) != 0) {
+    if (a.jacobi) {  // extension: the reference's bench wrapper only knows plain CG
+        std::vector<double> t;
+        for (int r = 0; r < a.runs; r++) {
+            std::fill(x.begin(), x.end(), 0.0);
+            if (solve(nullptr, &mat, b.data(), x.data(), r == 0 ? cfg : quiet, &st) != 0) { fprintf(stderr, "PCG solve failed\n"); return EXIT_FAILURE; }
+            t.push_back(st.time_total_ms);
+        }
+        std::sort(t.begin(), t.end());
+        bs.median_ms = t[t.size() / 2]; bs.mean_ms = 0; for (double v : t) bs.mean_ms += v / t.size();
+        bs.min_ms = t.front(); bs.max_ms = t.back(); bs.std_dev_ms = 0; bs.valid_runs = (int)t.size(); bs.outliers_removed = 0;
+    } else if (cg_benchmark_with_stats_mgpu_partitioned(nullptr, &mat, b.data(), x.data(), cfg, a.runs, &bs, &st) != 0) {
         fprintf(stderr, "CG benchmark failed\n");
         return EXIT_FAILURE;
     }
@@ -50,7 +67,7 @@ int main(int argc, char** argv) {
     printf("Sum(x):    %.16e\n", st.solution_sum);
     printf("Norm2(x):  %.16e\n", st.solution_norm);
     printf("=======================\n");
-    if (!a.json.empty()) export_cg_mgpu_json(a.json.c_str(), "partitioned-halo", &mat, &bs, &st, P);
+    if (!a.json.empty()) export_cg_mgpu_json(a.json.c_str(), a.jacobi ? "partitioned-halo-jacobi" : "partitioned-halo", &mat, &bs, &st, P);
     if (!a.csv.empty()) printf("CSV export is not implemented for the multi-GPU solver (as in the reference)\n");
     free(mat.entries);
     return EXIT_SUCCESS;

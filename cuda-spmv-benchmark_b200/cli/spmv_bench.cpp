@@ -1,4 +1,4 @@
-// spmv_bench <file.mtx | --grid=n> --mode=a[,b] [--json=F] [--csv=F]
+// spmv_bench <file.mtx | --grid=n> --mode=a[,b] [--json=F] [--csv=F] [--device-ingest]
 // reference src/main/main.cu:44-268: validate modes, load, x = 1, per mode init -> 5 warm-ups ->
 // benchmark_with_stats(10) -> checksums -> metrics -> JSON/CSV "<base>_<op><ext>" -> Sum/Norm2 lines.
 #include "cli_common.h"
@@ -17,7 +17,8 @@ int main(int argc, char** argv) {
             return EXIT_FAILURE;
         }
     MatrixData mat;
-    if (load_or_generate(a, &mat)) return EXIT_FAILURE;
+    void* d_entries = nullptr;
+    if (load_or_generate(a, &mat, &d_entries)) return EXIT_FAILURE;
     printf("Matrix loaded: %d rows, %d cols, %d nonzeros\n", mat.rows, mat.cols, mat.nnz);
     printf("Testing %zu mode(s): ", a.modes.size());
     for (size_t i = 0; i < a.modes.size(); i++) printf("%s%s", a.modes[i].c_str(), i + 1 < a.modes.size() ? ", " : "\n");
@@ -25,7 +26,7 @@ int main(int argc, char** argv) {
     for (auto& m : a.modes) {
         SpmvOperator* op = get_operator(m.c_str());
         printf("\n=== Testing mode: %s ===\n", m.c_str());
-        if (op->init(&mat) != 0) {
+        if (init_operator(op, &mat, d_entries) != 0) {
             fprintf(stderr, "Failed to initialize operator '%s'\n", op->name);
             return EXIT_FAILURE;
         }
@@ -78,5 +79,6 @@ int main(int argc, char** argv) {
     }
     if (a.modes.size() > 1) printf("\n=== Multi-mode benchmark completed ===\n");
     free(mat.entries);
+    if (d_entries) b200_free_device(d_entries);
     return EXIT_SUCCESS;
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/b200_kernels.h"
 #include "cg_kernels.cuh"
@@ -13,6 +14,10 @@
 #include "ingest.cuh"
 #include "stencil5.cuh"
 #include "stencil_layout.h"
+
+#ifndef B200_PDL_DEFAULT
+#define B200_PDL_DEFAULT 3
+#endif
 
 using namespace b200;
 
@@ -42,6 +47,36 @@ extern "C" const char* b200_version(void) { return "b200-spmv-cg 0.1 (sm_100a)";
 extern "C" const char* b200_last_error(void) { return g_err; }
 extern "C" unsigned long long b200_launch_count(void) { return g_launches.load(); }
 
+namespace {
+// programmatic dependent launch, bit 0: the small kernels of the loop (reduce, halo direction, finish_x),
+// bit 1: the STENCIL5 kernels.  B200_PDL=<0..3>, b200_cg_set_pdl().
+std::atomic<int> g_pdl{-1};
+int pdl_mode() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("B200_PDL");
+        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : B200_PDL_DEFAULT;
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// Launch with programmatic stream serialisation: the kernel may be scheduled while the previous
+// kernel of the stream drains; it calls griddep_wait() before it reads anything.
+template <int BIT = 1, typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mode() & BIT) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------
 // STENCIL5
 // ------------------------------------------------------------------------------------------------
@@ -70,9 +105,16 @@ const Variant kVariants[] = {
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 const int kDefaultRowsPerItem = 8;
+constexpr int kMaxDevices = 64;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
 
 struct Geometry {
     Stencil5Args a;
+    TailArgs tail;  // what follows the launch: fixed-order sum of the partials + exchange + recurrence (cg_reduce_kernel)
     int grid;
     int threads;
     size_t smem;
@@ -90,6 +132,8 @@ int build_geometry(const b200_band* b, const double* x, Geometry* g) {
     const Variant& V = kVariants[v];
     Stencil5Args& a = g->a;
     memset(&a, 0, sizeof a);
+    memset(&g->tail, 0, sizeof g->tail);
+    g->tail.which = -1;
     a.row_ptr = b->layout == 0 ? b->d_row_ptr : nullptr;
     a.col_idx = b->d_col_idx;
     a.values = b->d_values;
@@ -130,6 +174,7 @@ int build_geometry(const b200_band* b, const double* x, Geometry* g) {
     a.flag_prev = b->d_flag_prev;
     a.flag_next = b->d_flag_next;
     a.epoch = b->epoch;
+    a.epoch_ptr = b->d_epoch_ptr;
     g->threads = V.warps * 32;
     const int nb = (a.n_boundary_rows + g->threads - 1) / g->threads;
     g->grid = a.n_interior_ctas + nb;
@@ -140,8 +185,11 @@ int build_geometry(const b200_band* b, const double* x, Geometry* g) {
 template <int MODE, int COLS, int WARPS, int STAGES, bool CG>
 int launch_one(const Geometry& g, cudaStream_t s) {
     auto k = stencil5_kernel<MODE, COLS, WARPS, STAGES, CG>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
+    // per instantiation AND per device: the shared-memory opt-in is a per-device function attribute
+    // (one process may drive several GPUs, cg_solver_mgpu_stencil --gpus=P)
+    static std::atomic<bool> attr_set[kMaxDevices];
+    const int dev = current_device();
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -149,9 +197,10 @@ int launch_one(const Geometry& g, cudaStream_t s) {
             return (e == cudaErrorNoKernelImageForDevice || e == cudaErrorInvalidDeviceFunction) ? B200_ENODEV
                                                                                                  : B200_ECUDA;
         }
-        attr_set = true;
+        attr_set[dev].store(true, std::memory_order_release);
     }
-    k<<<g.grid, g.threads, g.smem, s>>>(g.a);
+    if (MODE == ST_PLAIN) k<<<g.grid, g.threads, g.smem, s>>>(g.a);
+    else launch_pdl<2>(k, g.grid, g.threads, g.smem, s, g.a);
     return check_launch("stencil5_kernel");
 }
 
@@ -263,7 +312,10 @@ template <int WARPS, int STAGES, int WIN, int MODE, int MINB, bool DOT = false>
 int launch_csr_ring_mode(const CsrArgs& a, int gpw_override, cudaStream_t s) {
     auto k = csr_ring_kernel<WARPS, STAGES, WIN, MODE, MINB, DOT>;
     const size_t smem = (size_t)WARPS * csr_ring_warp_bytes<STAGES, WIN>();
-    static int resident_ctas = 0;  // per instantiation: CTAs that fit the whole GPU at once
+    // per instantiation and per device: CTAs that fit the whole GPU at once
+    static std::atomic<int> resident_tab[kMaxDevices];
+    const int dev_id = current_device();
+    int resident_ctas = resident_tab[dev_id].load(std::memory_order_acquire);
     if (resident_ctas == 0) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 0, dev = 0, n_sm = 0;
@@ -279,6 +331,7 @@ int launch_csr_ring_mode(const CsrArgs& a, int gpw_override, cudaStream_t s) {
                        : B200_ECUDA;
         }
         resident_ctas = occ * n_sm;
+        resident_tab[dev_id].store(resident_ctas, std::memory_order_release);
     }
     // one item (run of 32-row groups) per warp, handed out in launch order; small matrices get
     // shorter items so that every SM has work
@@ -487,63 +540,158 @@ extern "C" size_t b200_cg_status_bytes(void) { return sizeof(CGStatus); }
 extern "C" size_t b200_xchg_bytes(void) { return sizeof(XchgArea); }
 extern "C" size_t b200_xchg_flag_prev_offset(void) { return offsetof(XchgArea, halo_flag_prev); }
 extern "C" size_t b200_xchg_flag_next_offset(void) { return offsetof(XchgArea, halo_flag_next); }
+extern "C" size_t b200_xchg_halo_seq_offset(void) { return offsetof(XchgArea, halo_seq); }
 
 namespace {
-constexpr int kBlas1Ctas = 148 * 8;  // 8 resident 256-thread CTAs per SM, one wave
-inline int blas1_grid(long long n, int vec, int cap = kBlas1Ctas) {
-    const long long tile = 256LL * vec * 4;
-    long long need = (n + tile - 1) / tile;
-    if (need < 1) need = 1;
-    return (int)(need < cap ? need : cap);
-}
+constexpr int kBlas1CtasPerSm = 8;  // resident 256-thread CTAs per SM, one wave
 // K2 / K2r (two or four input streams, unrolled double2 loads): 2 CTAs per SM measured best on B200
 // (1.503 vs 1.555 ms for 24 B/row at 20k x 20k).  Both kernels MUST use the same grid: their r.r
 // partials are summed in the same order, which keeps the two CG schedules bit-identical.
-constexpr int kRrCtas = 148 * 2;
+constexpr int kRrCtasPerSm = 2;
+int sm_count() {  // per device (a process may drive several GPUs)
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+inline int blas1_grid(long long n, int vec, int ctas_per_sm = kBlas1CtasPerSm) {
+    const long long tile = 256LL * vec * 4;
+    long long need = (n + tile - 1) / tile;
+    if (need < 1) need = 1;
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    return (int)(need < cap ? need : cap);
+}
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// The persistent BLAS-1 kernels (K2 / K2r / K3) split their work statically over sm_count * 2 CTAs, which
+// only balances if every SM hosts exactly two of them.  A normal launch spreads the CTAs breadth-first; a
+// programmatic (dependent) launch places them as resources free up and stacks three or four on some SMs
+// (measured at 20k x 20k: K2r 1.507 -> 1.583 ms; capping the residency with 100 KB of dummy shared
+// memory per CTA shrinks L1 and costs more: 1.87 ms).  They are therefore launched the normal way: one
+// launch gap per iteration stays, in front of K2 / K2r.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// device view of a reduction context.  grid = CTAs of the producing launch (one partial each).
+int make_tail(const b200_reduce_ctx* c, int which, int two, long long grid, TailArgs* t, const char* who) {
+    memset(t, 0, sizeof *t);
+    t->which = -1;
+    if (!c) return fail(B200_EINVAL, "%s: NULL reduction context", who);
+    if (!c->d_partials || grid > c->capacity || (two && !c->d_partials_b))
+        return fail(B200_EINVAL, "%s: partials buffer missing or too small", who);
+    if (which != RED_SUM && !c->d_scalars) return fail(B200_EINVAL, "%s: NULL scalars", who);
+    t->partials = c->d_partials; t->partials_b = c->d_partials_b; t->two = two;
+    t->sc = static_cast<CGScalars*>(c->d_scalars);
+    if (c->phases == 0) return B200_OK;  // partials only: tickets stay NULL
+    if (!c->d_group_sums || !c->d_tickets) return fail(B200_EINVAL, "%s: NULL group sums / tickets", who);
+    if (c->world < 1 || c->world > B200_MAX_RANKS || c->rank < 0 || c->rank >= c->world)
+        return fail(B200_EINVAL, "%s: bad rank / world", who);
+    if (c->world > 1 && !c->d_peer_xchg) return fail(B200_EINVAL, "%s: NULL peer table", who);
+    if (which == RED_SUM && !c->d_out) return fail(B200_EINVAL, "%s: NULL out", who);
+    if (c->phases != 3 && !c->d_stash) return fail(B200_EINVAL, "%s: split phases need a stash", who);
+    t->which = which; t->phases = c->phases; t->tol = c->tol;
+    t->status = static_cast<CGStatus*>(c->h_status_mapped);
+    t->out = c->d_out; t->stash = c->d_stash;
+    t->gsum = c->d_group_sums; t->tickets = c->d_tickets;
+    t->cap_groups = (int)((c->capacity + B200_RED_GROUP - 1) / B200_RED_GROUP);
+    t->rank = c->rank; t->world = c->world;
+    if (c->world > 1) {
+        for (int r = 0; r < c->world; r++) t->peer_xchg[r] = static_cast<XchgArea*>(c->d_peer_xchg[r]);
+        t->my_xchg = t->peer_xchg[c->rank];
+    }
+    return B200_OK;
+}
+
+// the stand-alone reduction over n partials (one warp-sized CTA per group of 256)
+int launch_reduce(const TailArgs& t, int n_partials, cudaStream_t s) {
+    ReduceArgs a;
+    a.t = t;
+    a.n_partials = n_partials;
+    int grid = (n_partials + B200_RED_GROUP - 1) / B200_RED_GROUP;
+    if (grid < 1) grid = 1;
+    launch_pdl(cg_reduce_kernel, grid, 32, 0, s, a);
+    return check_launch("cg_reduce_kernel");
+}
+
+// STENCIL5 producer + its reduction: the kernel writes one partial per CTA, cg_reduce_kernel follows
+// (programmatic dependent launch) unless the caller asked for the partials only
+template <int MODE>
+int launch_stencil_cg(const b200_band* band, Geometry& g, cudaStream_t s) {
+    TailArgs t = g.tail;
+    int rc = launch_stencil<MODE>(band, g, s);
+    if (rc || t.tickets == nullptr) return rc;
+    return launch_reduce(t, g.grid, s);
+}
+
+int make_push(const b200_halo_push_args* h, long long n, const double* v, const void* scalars, HaloPushArgs* a,
+              const char* who) {
+    memset(a, 0, sizeof *a);
+    if (!h) return B200_OK;
+    if (!h->d_my_xchg || h->halo < 1 || n < h->halo) return fail(B200_EINVAL, "%s: bad halo push arguments", who);
+    if ((h->d_dst_prev && !h->d_flag_prev) || (h->d_dst_next && !h->d_flag_next)) return fail(B200_EINVAL, "%s: NULL flag", who);
+    a->v_local = v; a->n_local = n; a->halo = h->halo; a->dst_prev = h->d_dst_prev; a->dst_next = h->d_dst_next;
+    a->flag_prev = h->d_flag_prev; a->flag_next = h->d_flag_next;
+    a->my_xchg = static_cast<XchgArea*>(h->d_my_xchg);
+    a->sc = static_cast<const CGScalars*>(scalars);
+    return B200_OK;
+}
 }  // namespace
+
+extern "C" void b200_cg_set_pdl(int mode) { g_pdl.store(mode & 3, std::memory_order_relaxed); }
 
 extern "C" int b200_cg_max_partials(const b200_band* band) {
     int n = b200_stencil5_num_partials(band);
     if (n < 0) return n;
-    return n > kBlas1Ctas ? n : kBlas1Ctas;
+    const int blas1 = sm_count() * kBlas1CtasPerSm;
+    return n > blas1 ? n : blas1;
 }
 
 extern "C" int b200_cg_residual_init(const b200_band* band, const double* d_x, const double* d_b, double* d_r,
-                                     double* d_p, double* d_partials, void* d_scalars, b200_stream stream) {
+                                     double* d_p, const b200_reduce_ctx* ctx, b200_stream stream) {
     Geometry g;
     int rc = build_geometry(band, d_x, &g);
     if (rc) return rc;
-    if (!d_b || !d_r || !d_p || !d_partials) return fail(B200_EINVAL, "cg_residual_init: NULL argument");
-    g.a.y = d_r; g.a.y2 = d_p; g.a.b = d_b; g.a.partials = d_partials;
-    if (d_scalars) g.a.error_word = &static_cast<CGScalars*>(d_scalars)->error;
-    return launch_stencil<ST_RESID>(band, g, (cudaStream_t)stream);
+    if (!d_b || !d_r || !d_p) return fail(B200_EINVAL, "cg_residual_init: NULL argument");
+    if ((rc = make_tail(ctx, RED_RR0, 0, g.grid, &g.tail, "cg_residual_init"))) return rc;
+    g.a.y = d_r; g.a.y2 = d_p; g.a.b = d_b; g.a.partials = ctx->d_partials;
+    g.a.error_word = &static_cast<CGScalars*>(ctx->d_scalars)->error;
+    return launch_stencil_cg<ST_RESID>(band, g, (cudaStream_t)stream);
 }
 
-extern "C" int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double* d_Ap, double* d_partials,
-                                const void* d_scalars, b200_stream stream) {
+extern "C" int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double* d_Ap, const b200_reduce_ctx* ctx,
+                                b200_stream stream) {
     Geometry g;
     int rc = build_geometry(band, d_p, &g);
     if (rc) return rc;
-    if (!d_Ap || !d_partials) return fail(B200_EINVAL, "cg_spmv_dot: NULL argument");
-    g.a.y = d_Ap; g.a.partials = d_partials;
-    if (d_scalars) {
-        g.a.converged = &static_cast<const CGScalars*>(d_scalars)->converged;
-        g.a.error_word = &const_cast<CGScalars*>(static_cast<const CGScalars*>(d_scalars))->error;
-    }
-    return launch_stencil<ST_DOT>(band, g, (cudaStream_t)stream);
+    if (!d_Ap) return fail(B200_EINVAL, "cg_spmv_dot: NULL argument");
+    if ((rc = make_tail(ctx, RED_PAP, 0, g.grid, &g.tail, "cg_spmv_dot"))) return rc;
+    g.a.y = d_Ap; g.a.partials = ctx->d_partials;
+    CGScalars* sc = static_cast<CGScalars*>(ctx->d_scalars);
+    g.a.converged = &sc->converged;
+    g.a.error_word = &sc->error;
+    return launch_stencil_cg<ST_DOT>(band, g, (cudaStream_t)stream);
 }
 
-extern "C" int b200_cg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
-                                 double* d_x, double* d_r, double* d_partials, int* n_partials_out,
-                                 b200_stream stream) {
-    if (!d_scalars || !d_p || !d_Ap || !d_x || !d_r || !d_partials) return fail(B200_EINVAL, "cg_update_xr: NULL argument");
+extern "C" int b200_cg_update_xr(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r,
+                                 const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_p || !d_Ap || !d_x || !d_r) return fail(B200_EINVAL, "cg_update_xr: NULL argument");
     const bool v2 = aligned16(d_p) && aligned16(d_Ap) && aligned16(d_x) && aligned16(d_r);
-    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtas);
-    if (n_partials_out) *n_partials_out = grid;
-    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
-    if (v2) cg_update_xr_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_p, d_Ap, d_x, d_r, d_partials);
-    else cg_update_xr_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_p, d_Ap, d_x, d_r, d_partials);
+    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtasPerSm);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_RR, 0, grid, &t, "cg_update_xr");
+    if (rc) return rc;
+    const CGScalars* sc = static_cast<const CGScalars*>(ctx->d_scalars);
+    if (v2) launch_plain(cg_update_xr_kernel<2>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_p, d_Ap, d_x, d_r, t);
+    else launch_plain(cg_update_xr_kernel<1>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_p, d_Ap, d_x, d_r, t);
     return check_launch("cg_update_xr_kernel");
 }
 
@@ -551,103 +699,87 @@ extern "C" int b200_cg_update_p(long long n, const void* d_scalars, const double
                                 b200_stream stream) {
     if (!d_scalars || !d_r || !d_p) return fail(B200_EINVAL, "cg_update_p: NULL argument");
     const bool v2 = aligned16(d_r) && aligned16(d_p);
-    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtas);
+    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtasPerSm);
     const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
-    if (v2) cg_update_p_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_r, d_p);
-    else cg_update_p_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(n, sc, d_r, d_p);
+    if (v2) launch_plain(cg_update_p_kernel<2>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_r, d_p);
+    else launch_plain(cg_update_p_kernel<1>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_r, d_p);
     return check_launch("cg_update_p_kernel");
 }
 
-extern "C" int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p, int halo,
-                                     double* d_dst_prev, double* d_dst_next, uint32_t* d_flag_prev,
-                                     uint32_t* d_flag_next, uint32_t epoch, void* d_my_xchg, b200_stream stream) {
-    if (!d_scalars || !d_r || !d_p || !d_my_xchg || halo < 1 || n < halo) return fail(B200_EINVAL, "cg_update_p_push: bad argument");
-    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "cg_update_p_push: NULL flag");
+extern "C" int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p,
+                                     const b200_halo_push_args* h, b200_stream stream) {
+    if (!d_scalars || !d_r || !d_p || !h) return fail(B200_EINVAL, "cg_update_p_push: bad argument");
     HaloPushArgs a;
-    a.v_local = d_p; a.n_local = n; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
-    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
-    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
-    a.sc = static_cast<const CGScalars*>(d_scalars);
+    int rc = make_push(h, n, d_p, d_scalars, &a, "cg_update_p_push");
+    if (rc) return rc;
     const int grid = blas1_grid(n, 1);
-    cg_update_p_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, a.sc, d_r, d_p, a);
+    launch_pdl(cg_update_p_push_kernel, grid, 256, 0, (cudaStream_t)stream, n, a.sc, d_r, d_p, a);
     return check_launch("cg_update_p_push_kernel");
 }
 
 extern "C" int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
-                                  double* d_x, double* d_Ap, double* d_partials, const void* d_scalars,
-                                  b200_stream stream) {
+                                  double* d_x, double* d_Ap, const b200_reduce_ctx* ctx, b200_stream stream) {
     Geometry g;
     int rc = build_geometry(band, d_p_old, &g);
     if (rc) return rc;
-    if (!d_r || !d_p_new || !d_x || !d_Ap || !d_partials || !d_scalars) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
+    if (!d_r || !d_p_new || !d_x || !d_Ap || !ctx || !ctx->d_scalars) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
     if (d_p_new == d_p_old) return fail(B200_EINVAL, "cg_spmv_fused: p_new must not alias p_old");
-    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
-    g.a.y = d_Ap; g.a.y2 = d_p_new; g.a.r = d_r; g.a.xs = d_x; g.a.partials = d_partials;
+    if ((rc = make_tail(ctx, RED_PAP, 0, g.grid, &g.tail, "cg_spmv_fused"))) return rc;
+    const CGScalars* sc = static_cast<const CGScalars*>(ctx->d_scalars);
+    g.a.y = d_Ap; g.a.y2 = d_p_new; g.a.r = d_r; g.a.xs = d_x; g.a.partials = ctx->d_partials;
     g.a.ab = &sc->alpha;
     static_assert(offsetof(CGScalars, beta) == offsetof(CGScalars, alpha) + sizeof(double), "alpha, beta adjacent");
     g.a.converged = &sc->converged;
     g.a.error_word = &const_cast<CGScalars*>(sc)->error;
-    return launch_stencil<ST_FUSED>(band, g, (cudaStream_t)stream);
+    return launch_stencil_cg<ST_FUSED>(band, g, (cudaStream_t)stream);
 }
 
-namespace {
-int launch_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r, double* d_partials,
-                    int* n_partials_out, const HaloPushArgs* h, cudaStream_t s) {
+extern "C" int b200_cg_update_r(long long n, const double* d_Ap, double* d_r, const b200_halo_push_args* push,
+                                const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_Ap || !d_r) return fail(B200_EINVAL, "cg_update_r: NULL argument");
     const bool v2 = aligned16(d_Ap) && aligned16(d_r);
-    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtas);
-    if (n_partials_out) *n_partials_out = grid;
-    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
-    HaloPushArgs none;
-    memset(&none, 0, sizeof none);
-    if (h) {
-        if (v2) cg_update_r_kernel<2, true><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, *h);
-        else cg_update_r_kernel<1, true><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, *h);
+    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtasPerSm);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_RR, 0, grid, &t, "cg_update_r");
+    if (rc) return rc;
+    HaloPushArgs h;
+    if ((rc = make_push(push, n, d_r, ctx->d_scalars, &h, "cg_update_r"))) return rc;
+    if (push) {
+        if (!t.tickets) return fail(B200_EINVAL, "cg_update_r: the halo push needs a fused reduction (phases != 0)");
+        t.publish = 1; t.flag_prev = h.dst_prev ? h.flag_prev : nullptr; t.flag_next = h.dst_next ? h.flag_next : nullptr;
+        t.my_xchg = h.my_xchg;
+    }
+    const CGScalars* sc = static_cast<const CGScalars*>(ctx->d_scalars);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (push) {
+        if (v2) launch_plain(cg_update_r_kernel<2, true>, grid, 256, 0, s, n, sc, d_Ap, d_r, h, t);
+        else launch_plain(cg_update_r_kernel<1, true>, grid, 256, 0, s, n, sc, d_Ap, d_r, h, t);
     } else {
-        if (v2) cg_update_r_kernel<2, false><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, none);
-        else cg_update_r_kernel<1, false><<<grid, 256, 0, s>>>(n, sc, d_Ap, d_r, d_partials, none);
+        if (v2) launch_plain(cg_update_r_kernel<2, false>, grid, 256, 0, s, n, sc, d_Ap, d_r, h, t);
+        else launch_plain(cg_update_r_kernel<1, false>, grid, 256, 0, s, n, sc, d_Ap, d_r, h, t);
     }
     return check_launch("cg_update_r_kernel");
-}
-}  // namespace
-
-extern "C" int b200_cg_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
-                                double* d_partials, int* n_partials_out, b200_stream stream) {
-    if (!d_scalars || !d_Ap || !d_r || !d_partials) return fail(B200_EINVAL, "cg_update_r: NULL argument");
-    return launch_update_r(n, d_scalars, d_Ap, d_r, d_partials, n_partials_out, nullptr, (cudaStream_t)stream);
-}
-
-extern "C" int b200_cg_update_r_push(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
-                                     double* d_partials, int* n_partials_out, int halo, double* d_dst_prev,
-                                     double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next,
-                                     uint32_t epoch, void* d_my_xchg, b200_stream stream) {
-    if (!d_scalars || !d_Ap || !d_r || !d_partials || !d_my_xchg || halo < 1 || n < halo)
-        return fail(B200_EINVAL, "cg_update_r_push: bad argument");
-    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "cg_update_r_push: NULL flag");
-    HaloPushArgs a;
-    a.v_local = d_r; a.n_local = n; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
-    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
-    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
-    a.sc = static_cast<const CGScalars*>(d_scalars);
-    return launch_update_r(n, d_scalars, d_Ap, d_r, d_partials, n_partials_out, &a, (cudaStream_t)stream);
 }
 
 extern "C" int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const double* d_pold_prev,
                                 const double* d_pold_next, double* d_pnew_prev, double* d_pnew_next, int halo,
-                                const uint32_t* d_flag_prev, const uint32_t* d_flag_next, uint32_t epoch,
+                                const uint32_t* d_flag_prev, const uint32_t* d_flag_next, const void* d_my_xchg,
                                 void* d_scalars, int beta_zero, b200_stream stream) {
-    if (!d_scalars || halo < 1) return fail(B200_EINVAL, "cg_halo_dir: bad argument");
+    if (!d_scalars || halo < 1 || !d_my_xchg) return fail(B200_EINVAL, "cg_halo_dir: bad argument");
     if ((d_r_prev && (!d_pnew_prev || !d_flag_prev || (!beta_zero && !d_pold_prev))) ||
         (d_r_next && (!d_pnew_next || !d_flag_next || (!beta_zero && !d_pold_next))))
         return fail(B200_EINVAL, "cg_halo_dir: NULL buffer");
     if (!d_r_prev && !d_r_next) return B200_OK;
     HaloDirArgs a;
+    memset(&a, 0, sizeof a);
     a.r_prev = d_r_prev; a.r_next = d_r_next; a.pold_prev = d_pold_prev; a.pold_next = d_pold_next;
     a.pnew_prev = d_pnew_prev; a.pnew_next = d_pnew_next; a.halo = halo;
-    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
+    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next;
+    a.seq_ptr = &static_cast<const XchgArea*>(d_my_xchg)->halo_seq;
     a.sc = static_cast<CGScalars*>(d_scalars); a.beta_zero = beta_zero;
     int grid = (halo + 255) / 256;
     if (grid > 64) grid = 64;
-    cg_halo_dir_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    launch_pdl(cg_halo_dir_kernel, grid, 256, 0, (cudaStream_t)stream, a);
     return check_launch("cg_halo_dir_kernel");
 }
 
@@ -655,59 +787,32 @@ extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double
                                 double* d_x, b200_stream stream) {
     if (!d_scalars || !d_p0 || !d_p1 || !d_x) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
     const int grid = blas1_grid(n, 1);
-    cg_finish_x_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x);
+    launch_pdl(cg_finish_x_kernel, grid, 256, 0, (cudaStream_t)stream, n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x);
     return check_launch("cg_finish_x_kernel");
 }
 
-namespace {
-int launch_reduce(const double* d_partials, int n_partials, int which, int phases, double tol, void* d_scalars,
-                  void* h_status_mapped, double* d_out, int rank, int world, uint32_t epoch, void* const* d_peer_xchg,
-                  double* d_stash, const HaloDirArgs* hd, cudaStream_t stream) {
-    if (!d_partials || n_partials < 0) return fail(B200_EINVAL, "cg_reduce: bad partials");
-    if (which != RED_SUM && !d_scalars) return fail(B200_EINVAL, "cg_reduce: NULL scalars");
-    if (which == RED_SUM && !d_out) return fail(B200_EINVAL, "cg_reduce: NULL out");
-    if (world < 1 || world > B200_MAX_RANKS || rank < 0 || rank >= world) return fail(B200_EINVAL, "cg_reduce: bad rank/world");
-    if (world > 1 && !d_peer_xchg) return fail(B200_EINVAL, "cg_reduce: NULL peer table");
-    if (phases != 3 && !d_stash) return fail(B200_EINVAL, "cg_reduce: split phases need a stash");
-    ReduceArgs a;
-    memset(&a, 0, sizeof a);
-    a.partials = d_partials; a.n_partials = n_partials; a.which = which; a.phases = phases; a.tol = tol;
-    a.sc = static_cast<CGScalars*>(d_scalars);
-    a.status = static_cast<CGStatus*>(h_status_mapped);
-    a.out = d_out; a.rank = rank; a.world = world; a.epoch = epoch; a.stash = d_stash;
-    if (world > 1) {
-        for (int r = 0; r < world; r++) a.peer_xchg[r] = static_cast<XchgArea*>(d_peer_xchg[r]);
-        a.my_xchg = a.peer_xchg[rank];
-    }
-    if (hd) { a.with_halo_dir = 1; a.hd = *hd; }
-    cg_reduce_kernel<<<1, 1024, 0, stream>>>(a);
-    return check_launch("cg_reduce_kernel");
-}
-}  // namespace
-
-extern "C" int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
-                              void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
-                              uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream) {
-    return launch_reduce(d_partials, n_partials, which, phases, tol, d_scalars, h_status_mapped, d_out, rank, world, epoch,
-                         d_peer_xchg, d_stash, nullptr, (cudaStream_t)stream);
+extern "C" int b200_cg_reduce(const b200_reduce_ctx* ctx, int which, int n_partials, int two_sums, int phases,
+                              b200_stream stream) {
+    if (!ctx || n_partials < 0) return fail(B200_EINVAL, "cg_reduce: bad argument");
+    if (phases < 1 || phases > 3) return fail(B200_EINVAL, "cg_reduce: phases must be 1, 2 or 3");
+    b200_reduce_ctx c = *ctx;
+    c.phases = phases;
+    if (n_partials == 0 && !c.d_partials) c.d_partials = c.d_stash;  // exchange without data (barrier)
+    TailArgs t;
+    int rc = make_tail(&c, which, two_sums, n_partials, &t, "cg_reduce");
+    if (rc) return rc;
+    return launch_reduce(t, n_partials, (cudaStream_t)stream);
 }
 
-extern "C" int b200_cg_reduce_rr_dir(const double* d_partials, int n_partials, int phases, double tol, void* d_scalars,
-                                     void* h_status_mapped, int rank, int world, uint32_t epoch,
-                                     void* const* d_peer_xchg, double* d_stash, const double* d_r_prev,
-                                     const double* d_r_next, const double* d_pold_prev, const double* d_pold_next,
-                                     double* d_pnew_prev, double* d_pnew_next, int halo, const uint32_t* d_flag_prev,
-                                     const uint32_t* d_flag_next, uint32_t halo_epoch, b200_stream stream) {
-    if (halo < 1) return fail(B200_EINVAL, "cg_reduce_rr_dir: bad halo");
-    if ((d_r_prev && (!d_pnew_prev || !d_flag_prev || !d_pold_prev)) || (d_r_next && (!d_pnew_next || !d_flag_next || !d_pold_next)))
-        return fail(B200_EINVAL, "cg_reduce_rr_dir: NULL buffer");
-    HaloDirArgs h;
-    h.r_prev = d_r_prev; h.r_next = d_r_next; h.pold_prev = d_pold_prev; h.pold_next = d_pold_next;
-    h.pnew_prev = d_pnew_prev; h.pnew_next = d_pnew_next; h.halo = halo;
-    h.flag_prev = d_flag_prev; h.flag_next = d_flag_next; h.epoch = halo_epoch;
-    h.sc = static_cast<CGScalars*>(d_scalars); h.beta_zero = 0;
-    return launch_reduce(d_partials, n_partials, RED_RR, phases, tol, d_scalars, h_status_mapped, nullptr, rank, world,
-                         epoch, d_peer_xchg, d_stash, (d_r_prev || d_r_next) ? &h : nullptr, (cudaStream_t)stream);
+extern "C" int b200_cg_read_tail_times(const void* d_scalars, b200_cg_tail_times* h_out, b200_stream stream) {
+    if (!d_scalars || !h_out) return fail(B200_EINVAL, "cg_read_tail_times: NULL argument");
+    CGScalars h;
+    cudaError_t e = cudaMemcpyAsync(&h, d_scalars, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(B200_ECUDA, "cg_read_tail_times: %s", cudaGetErrorString(e));
+    for (int k = 0; k < 8; k++) { h_out->ns[k] = h.tail_ns[k]; h_out->count[k] = h.tail_cnt[k]; h_out->gap_ns[k] = h.gap_ns[k]; }
+    h_out->error = h.error;
+    return B200_OK;
 }
 
 // ---- Jacobi-preconditioned CG ----
@@ -721,85 +826,78 @@ extern "C" int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, con
     return check_launch("pcg_diag_inv_kernel");
 }
 
-extern "C" int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, double* d_partials,
-                             int* n_partials_out, b200_stream stream) {
-    if (!d_r || !d_dinv || !d_p || !d_partials) return fail(B200_EINVAL, "pcg_init: NULL argument");
+extern "C" int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, const b200_reduce_ctx* ctx,
+                             b200_stream stream) {
+    if (!d_r || !d_dinv || !d_p) return fail(B200_EINVAL, "pcg_init: NULL argument");
     const int grid = blas1_grid(n, 1);
-    if (n_partials_out) *n_partials_out = grid;
-    pcg_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_r, d_dinv, d_p, d_partials);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_RZ0, 0, grid, &t, "pcg_init");
+    if (rc) return rc;
+    pcg_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_r, d_dinv, d_p, t);
     return check_launch("pcg_init_kernel");
 }
 
-extern "C" int b200_pcg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
-                                  const double* d_dinv, double* d_x, double* d_r, double* d_partials_rr,
-                                  double* d_partials_rz, int* n_partials_out, b200_stream stream) {
-    if (!d_scalars || !d_p || !d_Ap || !d_dinv || !d_x || !d_r || !d_partials_rr || !d_partials_rz)
-        return fail(B200_EINVAL, "pcg_update_xr: NULL argument");
+extern "C" int b200_pcg_update_xr(long long n, const double* d_p, const double* d_Ap, const double* d_dinv, double* d_x,
+                                  double* d_r, const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_p || !d_Ap || !d_dinv || !d_x || !d_r) return fail(B200_EINVAL, "pcg_update_xr: NULL argument");
     const int grid = blas1_grid(n, 1);
-    if (n_partials_out) *n_partials_out = grid;
-    pcg_update_xr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_p, d_Ap, d_dinv,
-                                                                 d_x, d_r, d_partials_rr, d_partials_rz);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_PCG, 1, grid, &t, "pcg_update_xr");
+    if (rc) return rc;
+    pcg_update_xr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(ctx->d_scalars), d_p, d_Ap,
+                                                                 d_dinv, d_x, d_r, t);
     return check_launch("pcg_update_xr_kernel");
 }
 
 extern "C" int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
-                                 b200_stream stream) {
+                                 const b200_halo_push_args* push, b200_stream stream) {
     if (!d_scalars || !d_r || !d_dinv || !d_p) return fail(B200_EINVAL, "pcg_update_p: NULL argument");
+    HaloPushArgs h;
+    int rc = make_push(push, n, d_p, d_scalars, &h, "pcg_update_p");
+    if (rc) return rc;
     pcg_update_p_kernel<<<blas1_grid(n, 1), 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_r,
-                                                                            d_dinv, d_p);
+                                                                            d_dinv, d_p, h);
     return check_launch("pcg_update_p_kernel");
 }
 
-extern "C" int b200_pcg_reduce(const double* d_partials_rr, const double* d_partials_rz, int n_partials, double tol,
-                               void* d_scalars, void* h_status_mapped, b200_stream stream) {
-    if (!d_partials_rr || !d_partials_rz || n_partials < 0 || !d_scalars) return fail(B200_EINVAL, "pcg_reduce: bad argument");
-    ReduceArgs a;
-    memset(&a, 0, sizeof a);
-    a.partials = d_partials_rr; a.partials_b = d_partials_rz; a.n_partials = n_partials; a.which = RED_PCG; a.phases = 3;
-    a.tol = tol; a.sc = static_cast<CGScalars*>(d_scalars); a.status = static_cast<CGStatus*>(h_status_mapped);
-    a.rank = 0; a.world = 1;
-    cg_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
-    return check_launch("cg_reduce_kernel");
-}
-
-extern "C" int b200_dot_partials(long long n, const void* d_scalars, const double* d_x, const double* d_y,
-                                 double* d_partials, int* n_partials_out, b200_stream stream) {
-    if (!d_x || !d_y || !d_partials) return fail(B200_EINVAL, "dot_partials: NULL argument");
+extern "C" int b200_dot_partials(long long n, const double* d_x, const double* d_y, const b200_reduce_ctx* ctx,
+                                 b200_stream stream) {
+    if (!d_x || !d_y) return fail(B200_EINVAL, "dot_partials: NULL argument");
     const int grid = blas1_grid(n, 1);
-    if (n_partials_out) *n_partials_out = grid;
-    dot_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(d_scalars), d_x, d_y,
-                                                                d_partials);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_PAP, 0, grid, &t, "dot_partials");
+    if (rc) return rc;
+    dot_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(ctx->d_scalars), d_x, d_y, t);
     return check_launch("dot_partials_kernel");
 }
 
 extern "C" int b200_residual_init_generic(long long n, const double* d_b, const double* d_Ap, double* d_r,
-                                          double* d_p, double* d_partials, int* n_partials_out, b200_stream stream) {
-    if (!d_b || !d_Ap || !d_r || !d_p || !d_partials) return fail(B200_EINVAL, "residual_init: NULL argument");
+                                          double* d_p, const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_b || !d_Ap || !d_r || !d_p) return fail(B200_EINVAL, "residual_init: NULL argument");
     const int grid = blas1_grid(n, 1);
-    if (n_partials_out) *n_partials_out = grid;
-    residual_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_b, d_Ap, d_r, d_p, d_partials);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_RR0, 0, grid, &t, "residual_init");
+    if (rc) return rc;
+    residual_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_b, d_Ap, d_r, d_p, t);
     return check_launch("residual_init_kernel");
 }
 
-extern "C" int b200_checksum_partials(long long n, const double* d_x, double* d_psum, double* d_psq,
-                                      int* n_partials_out, b200_stream stream) {
-    if (!d_x || !d_psum || !d_psq) return fail(B200_EINVAL, "checksum: NULL argument");
+extern "C" int b200_checksum(long long n, const double* d_x, const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_x) return fail(B200_EINVAL, "checksum: NULL argument");
     const int grid = blas1_grid(n, 1);
-    if (n_partials_out) *n_partials_out = grid;
-    checksum_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_x, d_psum, d_psq);
+    TailArgs t;
+    int rc = make_tail(ctx, RED_SUM, 1, grid, &t, "checksum");
+    if (rc) return rc;
+    checksum_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_x, t);
     return check_launch("checksum_partials_kernel");
 }
 
-extern "C" int b200_halo_push(const double* d_v_local, long long n_local, int halo, double* d_dst_prev,
-                              double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next, uint32_t epoch,
-                              void* d_my_xchg, const void* d_scalars, b200_stream stream) {
-    if (!d_v_local || !d_my_xchg || halo < 1 || n_local < halo) return fail(B200_EINVAL, "halo_push: bad argument");
-    if ((d_dst_prev && !d_flag_prev) || (d_dst_next && !d_flag_next)) return fail(B200_EINVAL, "halo_push: NULL flag");
+extern "C" int b200_halo_push(const double* d_v_local, long long n_local, const b200_halo_push_args* h,
+                              const void* d_scalars, b200_stream stream) {
+    if (!d_v_local || !h) return fail(B200_EINVAL, "halo_push: bad argument");
     HaloPushArgs a;
-    a.v_local = d_v_local; a.n_local = n_local; a.halo = halo; a.dst_prev = d_dst_prev; a.dst_next = d_dst_next;
-    a.flag_prev = d_flag_prev; a.flag_next = d_flag_next; a.epoch = epoch;
-    a.push_count = static_cast<XchgArea*>(d_my_xchg)->push_count;
-    a.sc = static_cast<const CGScalars*>(d_scalars);
+    int rc = make_push(h, n_local, d_v_local, d_scalars, &a, "halo_push");
+    if (rc) return rc;
     const int per_dir = 8;
     halo_push_kernel<<<2 * per_dir, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("halo_push_kernel");
@@ -891,7 +989,22 @@ int exclusive_scan(const T* d_in, long long* d_out, long long n, long long* d_to
 }
 }  // namespace
 
-extern "C" int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int* d_row_ptr, int* d_col_idx,
+extern "C" int b200_patch_entry_values(void* d_entries, const long long* h_pairs, int n, b200_stream stream) {
+    if (n <= 0) return B200_OK;
+    if (!d_entries || !h_pairs) return fail(B200_EINVAL, "patch_entry_values: NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf list;
+    if (list.alloc((size_t)n * 16) != cudaSuccess) { cudaGetLastError(); return fail(B200_ENOMEM, "patch_entry_values: cudaMalloc"); }
+    cudaError_t e = cudaMemcpyAsync(list.p, h_pairs, (size_t)n * 16, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail(B200_ECUDA, "patch_entry_values: %s", cudaGetErrorString(e));
+    patch_entry_values_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<EntryPOD*>(d_entries), list.as<long long>(), n);
+    int rc = check_launch("patch_entry_values_kernel");
+    if (rc) return rc;
+    e = cudaStreamSynchronize(s);  // list is freed on return
+    return e == cudaSuccess ? B200_OK : fail(B200_ECUDA, "patch_entry_values: %s", cudaGetErrorString(e));
+}
+
+extern "C" int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int cols, int* d_row_ptr, int* d_col_idx,
                                double* d_values, b200_stream stream) {
     if ((!d_entries && nnz > 0) || !d_row_ptr || rows < 0 || nnz < 0 || nnz > 2147483647LL)
         return fail(B200_EINVAL, "coo_to_csr: bad argument");
@@ -912,14 +1025,15 @@ extern "C" int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, i
     long long* total = misc.as<long long>();
     int rc;
     if (nnz > 0) {
-        coo_count_rows_kernel<<<gen_grid(nnz), 256, 0, s>>>(e, nnz, rows, counts.as<int>(), bad);
+        coo_count_rows_kernel<<<gen_grid(nnz), 256, 0, s>>>(e, nnz, rows, cols, counts.as<int>(), bad);
         if ((rc = check_launch("coo_count_rows_kernel"))) return rc;
     }
     if ((rc = exclusive_scan<int>(counts.as<int>(), scan.as<long long>(), rows, total, s))) return rc;
     int h_bad = 0;
     cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
-    if (h_bad) return fail(B200_EINVAL, "coo_to_csr: entry with a row index outside [0, rows)");
+    if (h_bad == 1) return fail(B200_EINVAL, "coo_to_csr: entry with a row index outside [0, rows)");
+    if (h_bad) return fail(B200_EINVAL, "coo_to_csr: entry with a column index outside [0, cols)");
     coo_finish_row_ptr_kernel<<<gen_grid(rows + 1), 256, 0, s>>>(scan.as<long long>(), nnz, rows, d_row_ptr, cursor.as<int>());
     if ((rc = check_launch("coo_finish_row_ptr_kernel"))) return rc;
     if (nnz > 0) {

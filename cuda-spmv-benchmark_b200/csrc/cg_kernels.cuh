@@ -30,11 +30,20 @@ struct CGScalars {
     int converged;
     int iterations;   // completed iterations (counts the converging one, cg_solver.cu:619)
     int error;        // a peer-flag wait timed out: later waits return at once
+    int pad_;
+    // device-measured duration of the reduction tails (final sum + rank exchange + scalar update),
+    // indexed by RED_*: what used to be separate cg_reduce launches
+    unsigned long long tail_ns[8];
+    unsigned int tail_cnt[8];
+    // ... and of what ran between the end of the previous tail and the begin of this one (the producing
+    // kernel(s) of this reduction): per-phase times that cost no events and no synchronisation
+    unsigned long long gap_ns[8];
+    unsigned long long last_tail_end;
 };
 
-// host-visible mirror (pinned, mapped), written by the reduce kernel after every r.r
+// host-visible mirror (pinned, mapped), written by the reduction tail after every r.r
 struct CGStatus {
-    volatile int iterations;
+    volatile int iterations;  // (iterations, converged): one aligned 8-byte word, stored at once; the host polls it
     volatile int converged;
     volatile double residual;
     volatile double b_norm;
@@ -43,10 +52,16 @@ struct CGStatus {
 
 // exchange area of one rank, in that rank's device memory, written by its peers over NVLink
 struct XchgArea {
-    uint64_t slots[2][B200_MAX_RANKS][2];  // LL words: (epoch << 32 | 32 data bits) x 2 per double
-    uint32_t halo_flag_prev;               // epoch of the last halo written by rank-1
-    uint32_t halo_flag_next;               // epoch of the last halo written by rank+1
+    uint64_t slots[2][B200_MAX_RANKS][4];  // LL words: (seq << 32 | 32 data bits) x 2 per double, 2 doubles
+    uint32_t halo_flag_prev;               // sequence number of the last halo written by rank-1
+    uint32_t halo_flag_next;               // sequence number of the last halo written by rank+1
     uint32_t push_count[2];                // local: CTAs done with the halo push (prev, next)
+    // Exchange sequence numbers live ON THE DEVICE: every rank executes the same sequence of
+    // exchanges (kernels turn into no-ops on all ranks at the same iteration once the solve has
+    // converged), so the counters stay in lockstep no matter how many no-op iterations each host
+    // enqueues behind the convergence point.
+    uint32_t red_seq;                      // scalar exchanges started by this rank
+    uint32_t halo_seq;                     // halo pushes published by this rank
     uint32_t pad[26];
 };
 
@@ -59,8 +74,7 @@ struct HaloPushArgs {
     double* dst_next;  // rank+1's halo_prev landing buffer (NULL if last rank)
     uint32_t* flag_prev;  // rank-1's halo_flag_next
     uint32_t* flag_next;  // rank+1's halo_flag_prev
-    uint32_t epoch;
-    uint32_t* push_count;  // my_xchg->push_count
+    XchgArea* my_xchg;    // push_count, halo_seq
     const CGScalars* sc;
 };
 
@@ -75,178 +89,291 @@ struct HaloDirArgs {
     int halo;
     const uint32_t* flag_prev;
     const uint32_t* flag_next;
-    uint32_t epoch;
+    const uint32_t* seq_ptr;  // my_xchg->halo_seq: the push every neighbour must have published
     CGScalars* sc;
     int beta_zero;
 };
 
 enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3, RED_RZ0 = 4, RED_PCG = 5 };  // 4, 5: Jacobi PCG
 enum { RED_PUSH = 1, RED_COMBINE = 2 };
+#define B200_RED_GROUP 256
 
-struct ReduceArgs {
-    const double* partials;
-    const double* partials_b;  // RED_PCG: the r.z partials (partials = r.r), same count; single rank only
-    int n_partials;
-    int which;   // RED_*
-    int phases;  // RED_PUSH | RED_COMBINE
+// Reduction context of a launch: where the per-CTA partial sums go and what happens to their total.
+// Fused form ("tail"): every CTA takes a ticket after writing its partial; the last CTA of each group
+// of 256 adds the group in a fixed order, the last group closer adds the group sums in a fixed order,
+// exchanges the total with the other ranks and applies the scalar recurrence `which` -- no separate
+// reduce launch.  The order of every addition is independent of which CTA happens to do it, so the
+// result is bit-reproducible and identical to cg_reduce_kernel over the same partials.
+struct TailArgs {
+    int which;    // RED_*; < 0: this launch only writes its partials (cg_reduce_kernel follows)
+    int phases;   // RED_PUSH: local total + LL stores to the peers; RED_COMBINE: wait + recurrence
+    int two;      // a second sum travels along (PCG r.z, checksum sum of squares)
     double tol;
     CGScalars* sc;
     CGStatus* status;  // may be NULL
-    double* out;       // RED_SUM: result
-    // multi-rank
+    double* out;       // RED_SUM: out[0] (and out[1]) receive the total(s)
+    double* stash;     // [2] local totals between a PUSH-only tail and the COMBINE launch
+    double* partials;
+    double* partials_b;
+    double* gsum;      // [2][cap_groups]
+    uint32_t* tickets; // [1 + cap_groups], zero between launches (self-resetting)
+    int cap_groups;
     int rank, world;
-    uint32_t epoch;
     XchgArea* my_xchg;
     XchgArea* peer_xchg[B200_MAX_RANKS];
-    double* stash;  // local: my partial sum between PUSH and COMBINE launches
-    // RED_RR, multi-GPU deferred-x schedule: once beta is known the same CTA advances the halo copies
-    // of the direction, p_halo = fma(beta, p_halo_old, r_halo) (one launch less per iteration)
-    int with_halo_dir;
-    HaloDirArgs hd;
+    // halo publication by the final CTA (kernels that push the edges of a vector to the neighbours)
+    int publish;
+    uint32_t* flag_prev;  // rank-1's halo_flag_next
+    uint32_t* flag_next;  // rank+1's halo_flag_prev
 };
 
-// One CTA of 1024 threads.  Fixed-order final sum of the per-CTA partials, optional rank
-// exchange (LL protocol: data and epoch travel in the same 8-byte store, so no fence), then the
-// scalar recurrences that the reference spreads over scalar_divide_kernel /
-// check_convergence_kernel / a D2D copy (cg_solver.cu:414-431,560,594-637).
-__global__ void __launch_bounds__(1024) cg_reduce_kernel(const ReduceArgs a) {
-    __shared__ double scratch[32];
-    __shared__ double rank_sum[B200_MAX_RANKS];
-    __shared__ double local_total;
-    CGScalars* sc = a.sc;
-    if (a.which != RED_SUM && sc->converged) return;
+// programmatic dependent launch: a kernel launched with the stream-serialisation attribute may be
+// scheduled while its predecessor drains; everything it reads must come after griddep_wait()
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-    const int t = threadIdx.x;
-    __shared__ double local_total_b;
-    if (a.phases & RED_PUSH) {
-        double v = 0.0;
-        for (int i = t; i < a.n_partials; i += 1024) v += a.partials[i];
-        v = block_sum(v, scratch);
-        if (t == 0) { local_total = v; if (a.stash) *a.stash = v; }
-        __syncthreads();
-        if (a.which == RED_PCG) {
-            double w = 0.0;
-            for (int i = t; i < a.n_partials; i += 1024) w += a.partials_b[i];
-            w = block_sum(w, scratch);
-            if (t == 0) local_total_b = w;
-            __syncthreads();
+// fixed-order sum of partials [first, first + 256) (clipped to n): lane l adds l, l+32, ... in order,
+// then the butterfly.  Warp-collective; every lane returns the sum.
+__device__ __forceinline__ double group_sum_fixed(const double* p, long long first, long long n) {
+    const int lane = threadIdx.x & 31;
+    double v[B200_RED_GROUP / 32];
+#pragma unroll
+    for (int j = 0; j < B200_RED_GROUP / 32; j++) {
+        const long long i = first + lane + 32 * j;
+        v[j] = (i < n) ? __ldcg(p + i) : 0.0;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < B200_RED_GROUP / 32; j++) s += v[j];
+    return warp_sum(s);
+}
+
+// fixed-order sum of n group sums: lane l adds l, l+32, ... in order, then the butterfly
+__device__ __forceinline__ double top_sum_fixed(const double* g, int n) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += __ldcg(g + i);
+    return warp_sum(s);
+}
+
+// Ticketed two-level reduction at the end of a producing kernel.  Called by ALL threads of every CTA
+// (blockDim.x >= 32) with the CTA's partial(s) valid in thread 0.  Returns true, in all threads of
+// exactly one CTA, once every CTA of the grid has contributed; tot[0..1] (shared) then hold the totals.
+__device__ __forceinline__ bool reduce_tickets(const TailArgs& t, double acc, double acc_b, double* tot, int* flags) {
+    const unsigned nb = gridDim.x;
+    const unsigned g = blockIdx.x / B200_RED_GROUP, ng = (nb + B200_RED_GROUP - 1) / B200_RED_GROUP;
+    if (threadIdx.x == 0) {
+        t.partials[blockIdx.x] = acc;
+        if (t.two) t.partials_b[blockIdx.x] = acc_b;
+        __threadfence();
+        const unsigned gsize = min((unsigned)B200_RED_GROUP, nb - g * B200_RED_GROUP);
+        flags[0] = (atomicAdd(&t.tickets[1 + g], 1u) + 1u == gsize);
+    }
+    __syncthreads();
+    if (!flags[0]) return false;
+    if (threadIdx.x < 32) {  // this CTA closes group g
+        __threadfence();
+        double s = group_sum_fixed(t.partials, (long long)g * B200_RED_GROUP, nb);
+        double sb = t.two ? group_sum_fixed(t.partials_b, (long long)g * B200_RED_GROUP, nb) : 0.0;
+        int last = 0;
+        if (threadIdx.x == 0) {
+            t.gsum[g] = s;
+            if (t.two) t.gsum[t.cap_groups + g] = sb;
+            t.tickets[1 + g] = 0;
+            __threadfence();
+            last = (atomicAdd(&t.tickets[0], 1u) + 1u == ng);
         }
+        last = __shfl_sync(B200_FULL, last, 0);
+        if (last) {  // ... and the grid
+            __threadfence();
+            s = top_sum_fixed(t.gsum, (int)ng);
+            sb = t.two ? top_sum_fixed(t.gsum + t.cap_groups, (int)ng) : 0.0;
+            if (threadIdx.x == 0) { tot[0] = s; tot[1] = sb; t.tickets[0] = 0; }
+        }
+        if (threadIdx.x == 0) flags[1] = last;
+    }
+    __syncthreads();
+    return flags[1] != 0;
+}
+
+// What the CTA holding the grand total does with it: publish the halo sequence number, exchange the
+// total with the other ranks (LL protocol: data and sequence number travel in the same 8-byte store,
+// so no fence; every rank adds the P slots in rank order => identical result everywhere), then the
+// scalar recurrences the reference spreads over scalar_divide_kernel / check_convergence_kernel / a
+// D2D copy (cg_solver.cu:414-431,560,594-637) and, multi-GPU, cublasDdot + MPI_Allreduce
+// (cg_solver_mgpu_partitioned.cu:145-154).  Called by all threads of one CTA (>= 32 threads).
+// sh: >= 2 * B200_MAX_RANKS + 4 doubles of shared memory.
+__device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double total_b, double* sh) {
+    const int t = threadIdx.x;
+    const uint64_t t_begin = globaltimer_ns();
+    CGScalars* sc = a.sc;
+    uint32_t* sh_seq = reinterpret_cast<uint32_t*>(sh + 2 * B200_MAX_RANKS);
+    if (a.publish && t == 0) {
+        // every CTA fenced its peer stores (system scope) before it took its ticket
+        const uint32_t hs = a.my_xchg->halo_seq + 1u;
+        a.my_xchg->halo_seq = hs;
+        __threadfence_system();
+        if (a.flag_prev != nullptr) st_release_sys(a.flag_prev, hs);
+        if (a.flag_next != nullptr) st_release_sys(a.flag_next, hs);
+    }
+    if (a.world > 1) {
+        if (t == 0) {
+            uint32_t seq = a.my_xchg->red_seq;
+            if (a.phases & RED_PUSH) { seq += 1u; a.my_xchg->red_seq = seq; }
+            *sh_seq = seq;
+        }
+        __syncthreads();
+    }
+    const uint32_t seq = (a.world > 1) ? *sh_seq : 0u;
+    if (a.phases & RED_PUSH) {
+        if (t == 0 && !(a.phases & RED_COMBINE)) { a.stash[0] = total; a.stash[1] = total_b; }
         if (a.world > 1 && t < a.world) {
-            const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
-            const uint64_t tag = (uint64_t)a.epoch << 32;
-            uint64_t* dst = a.peer_xchg[t]->slots[a.epoch & 1][a.rank];
+            const uint64_t tag = (uint64_t)seq << 32;
+            uint64_t* dst = a.peer_xchg[t]->slots[seq & 1][a.rank];
+            const uint64_t bits = (uint64_t)__double_as_longlong(total);
             st_volatile_u64(dst, tag | (bits & 0xffffffffull));
             st_volatile_u64(dst + 1, tag | (bits >> 32));
+            if (a.two) {
+                const uint64_t bits_b = (uint64_t)__double_as_longlong(total_b);
+                st_volatile_u64(dst + 2, tag | (bits_b & 0xffffffffull));
+                st_volatile_u64(dst + 3, tag | (bits_b >> 32));
+            }
         }
-    } else if (t == 0) {
-        local_total = *a.stash;
     }
     if (!(a.phases & RED_COMBINE)) return;
-    __syncthreads();
-
-    double total = local_total;
     if (a.world > 1) {
         if (t < a.world) {
-            const uint64_t* src = a.my_xchg->slots[a.epoch & 1][t];
+            const uint64_t* src = a.my_xchg->slots[seq & 1][t];
             const uint64_t t0 = globaltimer_ns();
             const bool dead = (sc != nullptr && sc->error != 0);
-            uint64_t w0, w1;
+            const int nw = a.two ? 4 : 2;
+            uint64_t w[4] = {0, 0, 0, 0};
             for (;;) {
-                w0 = ld_volatile_u64(src);
-                w1 = ld_volatile_u64(src + 1);
-                if ((uint32_t)(w0 >> 32) == a.epoch && (uint32_t)(w1 >> 32) == a.epoch) break;
+                bool ok = true;
+                for (int k = 0; k < nw; k++) {
+                    w[k] = ld_volatile_u64(src + k);
+                    ok = ok && ((uint32_t)(w[k] >> 32) == seq);
+                }
+                if (ok) break;
                 if (dead || globaltimer_ns() - t0 > 8000000000ull) {  // 8 s: report, never hang
                     if (sc) sc->error = 1;
                     if (a.status) a.status->error = 1;
                     break;
                 }
             }
-            rank_sum[t] = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            sh[t] = __longlong_as_double((long long)((w[1] << 32) | (w[0] & 0xffffffffull)));
+            sh[B200_MAX_RANKS + t] = __longlong_as_double((long long)((w[3] << 32) | (w[2] & 0xffffffffull)));
         }
         __syncthreads();
         if (t == 0) {
-            total = 0.0;
-            for (int r = 0; r < a.world; r++) total += rank_sum[r];  // rank order: same on every GPU
+            total = 0.0; total_b = 0.0;
+            for (int r = 0; r < a.world; r++) { total += sh[r]; total_b += sh[B200_MAX_RANKS + r]; }  // rank order
         }
     }
-    __shared__ int s_go_halo;
-    if (t == 0) {
-        s_go_halo = 0;
-        if (a.which == RED_SUM) {
-            *a.out = total;
-        } else if (a.which == RED_RR0) {
-            sc->rr_old = total;
-            sc->b_norm = sqrt(total);
-            sc->residual = sc->b_norm;
-            if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
-        } else if (a.which == RED_PAP) {
-            sc->pAp = total;
-            sc->alpha = sc->rr_old / total;  // PCG keeps rho = r.z in rr_old
-        } else if (a.which == RED_RZ0) {
-            sc->rr_old = total;  // rho_0 = r0.z0 (b_norm was set by RED_RR0)
+    if (t != 0) return;
+    if (a.which == RED_SUM) {
+        if (a.out) { a.out[0] = total; if (a.two) a.out[1] = total_b; }
+    } else if (a.which == RED_RR0) {
+        sc->rr_old = total;
+        sc->b_norm = sqrt(total);
+        sc->residual = sc->b_norm;
+        if (a.status) { a.status->b_norm = sc->b_norm; a.status->residual = sc->b_norm; }
+    } else if (a.which == RED_PAP) {
+        sc->pAp = total;
+        sc->alpha = sc->rr_old / total;  // PCG keeps rho = r.z in rr_old
+    } else if (a.which == RED_RZ0) {
+        sc->rr_old = total;  // rho_0 = r0.z0 (b_norm was set by RED_RR0)
+    } else {  // RED_RR, RED_PCG (total = r.r, total_b = r.z)
+        sc->rr_new = total;
+        const double res = sqrt(total);
+        sc->residual = res;
+        const int it = sc->iterations + 1;
+        sc->iterations = it;
+        const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
+        if (conv) {
+            sc->converged = 1;
         } else if (a.which == RED_PCG) {
-            sc->rr_new = total;
-            const double res = sqrt(total);
-            sc->residual = res;
-            const int it = sc->iterations + 1;
-            sc->iterations = it;
-            const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
-            if (conv) {
-                sc->converged = 1;
-            } else {
-                sc->beta = local_total_b / sc->rr_old;
-                sc->rr_old = local_total_b;
-            }
-            if (a.status) {
-                a.status->residual = res;
-                a.status->iterations = it;
-                a.status->converged = conv;
-            }
-        } else {  // RED_RR
-            sc->rr_new = total;
-            const double res = sqrt(total);
-            sc->residual = res;
-            const int it = sc->iterations + 1;
-            sc->iterations = it;
-            const int conv = (res / sc->b_norm < a.tol) ? 1 : 0;
-            if (conv) {
-                sc->converged = 1;
-            } else {
-                sc->beta = total / sc->rr_old;
-                sc->rr_old = total;
-                s_go_halo = a.with_halo_dir;
-            }
-            if (a.status) {
-                // the host reads these only after synchronising on an event recorded behind this
-                // kernel (cg_engine.cpp), so no system-scope fence is needed here
-                a.status->residual = res;
-                a.status->iterations = it;
-                a.status->converged = conv;
-            }
+            sc->beta = total_b / sc->rr_old;
+            sc->rr_old = total_b;
+        } else {
+            sc->beta = total / sc->rr_old;
+            sc->rr_old = total;
+        }
+        if (a.status) {
+            // (iterations, converged) travel in ONE 8-byte store: the host polls that word and needs no
+            // ordering against the other fields (it reads those after a stream synchronisation), so no
+            // system fence sits on the critical path between K2 and the next SpMV
+            a.status->residual = res;
+            if (sc->error) a.status->error = 1;
+            *reinterpret_cast<volatile unsigned long long*>(&a.status->iterations) =
+                (unsigned long long)(unsigned int)it | ((unsigned long long)(unsigned int)conv << 32);
         }
     }
-    if (!a.with_halo_dir) return;
-    __syncthreads();
-    if (!s_go_halo) return;
-    // ---- halo copies of the new direction (the neighbours' r edges arrived before their LL words)
-    const HaloDirArgs& h = a.hd;
-    if (t == 0) {
-        const uint64_t t0 = globaltimer_ns();
-        const uint32_t* fl[2] = {h.r_prev ? h.flag_prev : nullptr, h.r_next ? h.flag_next : nullptr};
-        for (int d = 0; d < 2; d++) {
-            if (!fl[d]) continue;
-            while ((int32_t)(ld_acquire_sys(fl[d]) - h.epoch) < 0) {
-                if (sc->error || globaltimer_ns() - t0 > 8000000000ull) { sc->error = 1; break; }
-                __nanosleep(64);
+    if (sc != nullptr && a.which >= 0 && a.which < 8) {
+        const uint64_t now = globaltimer_ns();
+        if (sc->last_tail_end != 0 && t_begin > sc->last_tail_end) sc->gap_ns[a.which] += t_begin - sc->last_tail_end;
+        sc->tail_ns[a.which] += now - t_begin;
+        sc->tail_cnt[a.which] += 1u;
+        sc->last_tail_end = now;
+    }
+}
+
+// end of a producing kernel: tickets, and the tail in the CTA that ends up with the total
+#define B200_TAIL_SHARED                                   \
+    __shared__ double tail_sh_[2 * B200_MAX_RANKS + 4];    \
+    __shared__ double tail_tot_[2];                        \
+    __shared__ int tail_flags_[2]
+#define B200_TAIL_FINISH(t, acc, acc_b)                                                   \
+    do {                                                                                  \
+        if ((t).tickets != nullptr && reduce_tickets((t), (acc), (acc_b), tail_tot_, tail_flags_)) \
+            cg_tail((t), tail_tot_[0], tail_tot_[1], tail_sh_);                           \
+    } while (0)
+
+// Stand-alone form: one warp-sized CTA per group of 256 partials adds its group, the last one to finish
+// adds the group sums and runs the tail -- the same two-level order as reduce_tickets.  Launched
+// programmatically behind the producing kernel (griddepcontrol: no launch gap).  Used behind the
+// STENCIL5 kernels (O(1e5) short CTAs: a ticket per producer CTA would cost more than this launch),
+// behind operators without a fused tail (run_device), for the COMBINE half when several ranks share
+// one device and one stream (a wait inside the producer could never be satisfied there), and for
+// exchanges without partials (barrier).  gridDim.x = max(1, ceil(n_partials / 256)).
+struct ReduceArgs {
+    TailArgs t;
+    int n_partials;
+};
+
+__global__ void __launch_bounds__(32) cg_reduce_kernel(const ReduceArgs a) {
+    __shared__ double sh[2 * B200_MAX_RANKS + 4];
+    griddep_wait();
+    const TailArgs& t = a.t;
+    if (t.which != RED_SUM && t.sc->converged) return;
+    griddep_launch();
+    const int lane = threadIdx.x;
+    double total = 0.0, total_b = 0.0;
+    if (t.phases & RED_PUSH) {
+        const int n = a.n_partials, ng = (n + B200_RED_GROUP - 1) / B200_RED_GROUP;
+        if (ng > 0) {
+            const int g = blockIdx.x;
+            const double s = group_sum_fixed(t.partials, (long long)g * B200_RED_GROUP, n);
+            const double sb = t.two ? group_sum_fixed(t.partials_b, (long long)g * B200_RED_GROUP, n) : 0.0;
+            int last = 0;
+            if (lane == 0) {
+                t.gsum[g] = s;
+                if (t.two) t.gsum[t.cap_groups + g] = sb;
+                __threadfence();
+                last = (atomicAdd(&t.tickets[0], 1u) + 1u == (unsigned)ng);
             }
+            last = __shfl_sync(B200_FULL, last, 0);
+            if (!last) return;
+            __threadfence();
+            total = top_sum_fixed(t.gsum, ng);
+            total_b = t.two ? top_sum_fixed(t.gsum + t.cap_groups, ng) : 0.0;
+            if (lane == 0) t.tickets[0] = 0;
         }
+    } else {
+        total = t.stash[0];
+        total_b = t.stash[1];
     }
-    __syncthreads();
-    const double beta = sc->beta;
-    for (int i = t; i < h.halo; i += 1024) {
-        if (h.r_prev) h.pnew_prev[i] = fma(beta, h.pold_prev[i], __ldcg(h.r_prev + i));
-        if (h.r_next) h.pnew_next[i] = fma(beta, h.pold_next[i], __ldcg(h.r_next + i));
-    }
+    cg_tail(t, total, total_b, sh);
 }
 
 // K2: x += alpha p ; r -= alpha Ap ; partials[cta] = sum r^2 over the CTA's tiles.
@@ -256,8 +383,10 @@ template <int VEC>
 __global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CGScalars* __restrict__ sc,
                                                            const double* __restrict__ p,
                                                            const double* __restrict__ Ap, double* __restrict__ x,
-                                                           double* __restrict__ r, double* __restrict__ partials) {
+                                                           double* __restrict__ r, const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
+    griddep_wait();
     if (sc->converged) return;
     const double alpha = sc->alpha, nalpha = -alpha;
     constexpr int UNROLL = 4;
@@ -312,8 +441,9 @@ __global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CG
             }
         }
     }
+    griddep_launch();
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    B200_TAIL_FINISH(tail, acc, 0.0);
 }
 
 // ---- "deferred x" schedule (4 launches, 112 B/row per iteration instead of 5 launches, 128 B/row) -------
@@ -327,8 +457,10 @@ __global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CG
 template <int VEC, bool PUSH>
 __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGScalars* __restrict__ sc,
                                                           const double* __restrict__ Ap, double* __restrict__ r,
-                                                          double* __restrict__ partials, const HaloPushArgs h) {
+                                                          const HaloPushArgs h, const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
+    griddep_wait();
     if (sc->converged) return;
     const double nalpha = -sc->alpha;
     constexpr int UNROLL = 4;
@@ -385,20 +517,12 @@ __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGS
             }
         }
     }
+    griddep_launch();
+    // the edge stores must be visible system-wide before this CTA's ticket: the CTA that ends up with
+    // the total publishes the halo sequence number to the neighbours (cg_tail)
     if (PUSH) __threadfence_system();
     acc = block_sum(acc, scratch);  // contains a __syncthreads
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = acc;
-        if (PUSH) {
-            const uint32_t done = atomicAdd(&h.push_count[0], 1u) + 1u;
-            if (done == gridDim.x) {
-                h.push_count[0] = 0;
-                __threadfence_system();
-                if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, h.epoch);
-                if (h.dst_next != nullptr) st_release_sys(h.flag_next, h.epoch);
-            }
-        }
-    }
+    B200_TAIL_FINISH(tail, acc, 0.0);
 }
 
 // Halo part of the direction update (multi-GPU, deferred-x schedule): the neighbours pushed the edges
@@ -407,13 +531,15 @@ __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGS
 // direction (p0 = r0).  One small CTA group; waits (bounded) for the arrival epochs first.
 
 __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
+    griddep_wait();
     if (a.sc->converged) return;
     if (threadIdx.x == 0) {
         const uint64_t t0 = globaltimer_ns();
+        const uint32_t epoch = __ldcg(a.seq_ptr);
         const uint32_t* fl[2] = {a.r_prev ? a.flag_prev : nullptr, a.r_next ? a.flag_next : nullptr};
         for (int d = 0; d < 2; d++) {
             if (!fl[d]) continue;
-            while ((int32_t)(ld_acquire_sys(fl[d]) - a.epoch) < 0) {
+            while ((int32_t)(ld_acquire_sys(fl[d]) - epoch) < 0) {
                 if (a.sc->error || globaltimer_ns() - t0 > 8000000000ull) { a.sc->error = 1; break; }
                 __nanosleep(64);
             }
@@ -432,6 +558,7 @@ __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
 __global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGScalars* __restrict__ sc,
                                                           const double* __restrict__ p0,
                                                           const double* __restrict__ p1, double* __restrict__ x) {
+    griddep_wait();
     const int it = sc->iterations;
     if (it <= 0) return;
     const double alpha = sc->alpha;
@@ -444,6 +571,7 @@ __global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGS
 template <int VEC>
 __global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
                                                           const double* __restrict__ r, double* __restrict__ p) {
+    griddep_wait();
     if (sc->converged) return;
     const double beta = sc->beta;
     constexpr int UNROLL = 4;
@@ -506,8 +634,9 @@ __global__ void __launch_bounds__(256) pcg_diag_inv_kernel(long long n_local, lo
 // after the residual init (r = b - A x0): p0 = z0 = dinv r0, partials of rho_0 = r0.z0
 __global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double* __restrict__ r,
                                                        const double* __restrict__ dinv, double* __restrict__ p,
-                                                       double* __restrict__ partials) {
+                                                       const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
     double acc = 0.0;
     const long long tile = 1024;
     for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
@@ -522,7 +651,7 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double
         }
     }
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    B200_TAIL_FINISH(tail, acc, 0.0);
 }
 
 // K2p: x += alpha p ; r -= alpha Ap ; partials of r.r (convergence) and r.z (rho), z = dinv r
@@ -530,9 +659,9 @@ __global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const C
                                                             const double* __restrict__ p,
                                                             const double* __restrict__ Ap,
                                                             const double* __restrict__ dinv, double* __restrict__ x,
-                                                            double* __restrict__ r, double* __restrict__ partials_rr,
-                                                            double* __restrict__ partials_rz) {
+                                                            double* __restrict__ r, const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
     if (sc->converged) return;
     const double alpha = sc->alpha, nalpha = -alpha;
     double arr = 0.0, arz = 0.0;
@@ -559,16 +688,21 @@ __global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const C
     arr = block_sum(arr, scratch);
     __syncthreads();
     arz = block_sum(arz, scratch);
-    if (threadIdx.x == 0) { partials_rr[blockIdx.x] = arr; partials_rz[blockIdx.x] = arz; }
+    B200_TAIL_FINISH(tail, arr, arz);
 }
 
-// K3p: p = z + beta p, z = dinv r
+// K3p: p = z + beta p, z = dinv r.  Multi-GPU (h.my_xchg != NULL): the first / last `halo` elements of
+// the new p also go into the neighbours' landing buffers, the last CTA publishes the sequence number
+// (same protocol as cg_update_p_push_kernel).
 __global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
                                                            const double* __restrict__ r,
-                                                           const double* __restrict__ dinv, double* __restrict__ p) {
+                                                           const double* __restrict__ dinv, double* __restrict__ p,
+                                                           const HaloPushArgs h) {
     if (sc->converged) return;
     const double beta = sc->beta;
     const long long tile = 1024;
+    const bool push = h.my_xchg != nullptr;
+    const long long next_lo = n - h.halo;
     for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
         double pv[4], rv[4], dv[4];
 #pragma unroll
@@ -579,7 +713,28 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CG
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const long long i = base + u * 256 + threadIdx.x;
-            if (i < n) p[i] = fma(beta, pv[u], dv[u] * rv[u]);
+            if (i < n) {
+                const double v = fma(beta, pv[u], dv[u] * rv[u]);
+                p[i] = v;
+                if (push) {
+                    if (h.dst_prev != nullptr && i < h.halo) h.dst_prev[i] = v;
+                    if (h.dst_next != nullptr && i >= next_lo) h.dst_next[i - next_lo] = v;
+                }
+            }
+        }
+    }
+    if (!push) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(&h.my_xchg->push_count[0], 1u) + 1u;
+        if (done == gridDim.x) {
+            h.my_xchg->push_count[0] = 0;
+            const uint32_t seq = h.my_xchg->halo_seq + 1u;
+            h.my_xchg->halo_seq = seq;
+            __threadfence_system();
+            if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, seq);
+            if (h.dst_next != nullptr) st_release_sys(h.flag_next, seq);
         }
     }
 }
@@ -588,8 +743,9 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CG
 // partial dot, r = b - Ap with p = r and r.r
 __global__ void __launch_bounds__(256) dot_partials_kernel(long long n, const CGScalars* __restrict__ sc,
                                                            const double* __restrict__ x, const double* __restrict__ y,
-                                                           double* __restrict__ partials) {
+                                                           const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
     if (sc != nullptr && sc->converged) return;
     double acc = 0.0;
     const long long tile = 1024;
@@ -601,13 +757,14 @@ __global__ void __launch_bounds__(256) dot_partials_kernel(long long n, const CG
         }
     }
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    B200_TAIL_FINISH(tail, acc, 0.0);
 }
 
 __global__ void __launch_bounds__(256) residual_init_kernel(long long n, const double* __restrict__ b,
                                                             const double* __restrict__ Ap, double* __restrict__ r,
-                                                            double* __restrict__ p, double* __restrict__ partials) {
+                                                            double* __restrict__ p, const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
     double acc = 0.0;
     const long long tile = 1024;
     for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
@@ -623,14 +780,15 @@ __global__ void __launch_bounds__(256) residual_init_kernel(long long n, const d
         }
     }
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    B200_TAIL_FINISH(tail, acc, 0.0);
 }
 
 // checksum partials: sum x and sum x^2 (fixed order); replaces the host loops at
 // cg_solver.cu:658-665 for vectors that never leave the device at 20k x 20k
 __global__ void __launch_bounds__(256) checksum_partials_kernel(long long n, const double* __restrict__ x,
-                                                                double* __restrict__ psum, double* __restrict__ psq) {
+                                                                const TailArgs tail) {
     __shared__ double scratch[8];
+    B200_TAIL_SHARED;
     double s = 0.0, q = 0.0;
     const long long tile = 1024;
     for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
@@ -643,7 +801,7 @@ __global__ void __launch_bounds__(256) checksum_partials_kernel(long long n, con
     s = block_sum(s, scratch);
     __syncthreads();
     q = block_sum(q, scratch);
-    if (threadIdx.x == 0) { psum[blockIdx.x] = s; psq[blockIdx.x] = q; }
+    B200_TAIL_FINISH(tail, s, q);
 }
 
 // Halo push: the first / last `halo` elements of the local vector go straight into the
@@ -656,17 +814,21 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
     const int per_dir = gridDim.x / 2;
     const int dir = blockIdx.x / per_dir, blk = blockIdx.x % per_dir;
     double* dst = dir == 0 ? a.dst_prev : a.dst_next;
-    if (dst == nullptr) return;
-    const double* src = dir == 0 ? a.v_local : a.v_local + (a.n_local - a.halo);
-    for (int i = blk * 256 + threadIdx.x; i < a.halo; i += per_dir * 256) dst[i] = src[i];
+    if (dst != nullptr) {
+        const double* src = dir == 0 ? a.v_local : a.v_local + (a.n_local - a.halo);
+        for (int i = blk * 256 + threadIdx.x; i < a.halo; i += per_dir * 256) dst[i] = src[i];
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t done = atomicAdd(&a.push_count[dir], 1u) + 1u;
-        if (done == (uint32_t)per_dir) {
-            a.push_count[dir] = 0;
+        const uint32_t done = atomicAdd(&a.my_xchg->push_count[0], 1u) + 1u;
+        if (done == gridDim.x) {  // last CTA: every rank publishes, also the ones at the ends of the chain
+            a.my_xchg->push_count[0] = 0;
+            const uint32_t seq = a.my_xchg->halo_seq + 1u;
+            a.my_xchg->halo_seq = seq;
             __threadfence_system();
-            st_release_sys(dir == 0 ? a.flag_prev : a.flag_next, a.epoch);
+            if (a.dst_prev != nullptr) st_release_sys(a.flag_prev, seq);
+            if (a.dst_next != nullptr) st_release_sys(a.flag_next, seq);
         }
     }
 }
@@ -678,6 +840,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
 __global__ void __launch_bounds__(256) cg_update_p_push_kernel(long long n, const CGScalars* __restrict__ sc,
                                                                const double* __restrict__ r, double* __restrict__ p,
                                                                const HaloPushArgs h) {
+    griddep_wait();
     if (sc->converged) return;
     const double beta = sc->beta;
     const long long tile = 1024;
@@ -700,15 +863,18 @@ __global__ void __launch_bounds__(256) cg_update_p_push_kernel(long long n, cons
             }
         }
     }
+    griddep_launch();
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t done = atomicAdd(&h.push_count[0], 1u) + 1u;
+        const uint32_t done = atomicAdd(&h.my_xchg->push_count[0], 1u) + 1u;
         if (done == gridDim.x) {
-            h.push_count[0] = 0;
+            h.my_xchg->push_count[0] = 0;
+            const uint32_t seq = h.my_xchg->halo_seq + 1u;
+            h.my_xchg->halo_seq = seq;
             __threadfence_system();
-            if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, h.epoch);
-            if (h.dst_next != nullptr) st_release_sys(h.flag_next, h.epoch);
+            if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, seq);
+            if (h.dst_next != nullptr) st_release_sys(h.flag_next, seq);
         }
     }
 }

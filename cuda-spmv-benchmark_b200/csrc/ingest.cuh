@@ -92,13 +92,23 @@ __global__ void __launch_bounds__(256) scan_add_offsets_kernel(long long* __rest
 }
 
 // ---------------------------------------------------------------- COO -> CSR
-__global__ void coo_count_rows_kernel(const EntryPOD* __restrict__ e, long long nnz, int rows,
+// cols > 0: column ids are range-checked as well (a malformed file must not make the x gather of the
+// SpMV kernels read out of bounds); bad: 1 = row, 2 = column outside the matrix
+__global__ void coo_count_rows_kernel(const EntryPOD* __restrict__ e, long long nnz, int rows, int cols,
                                       int* __restrict__ counts, int* __restrict__ bad) {
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x) {
-        const int r = e[k].row;
+        const int r = e[k].row, c = e[k].col;
         if (r < 0 || r >= rows) { atomicExch(bad, 1); continue; }
+        if (c < 0 || (cols > 0 && c >= cols)) { atomicMax(bad, 2); }
         atomicAdd(&counts[r], 1);
     }
+}
+
+// values re-read on the host (literals outside the exact fast path of the device parser): one staged
+// upload of (entry index, value bits) pairs, one launch
+__global__ void patch_entry_values_kernel(EntryPOD* __restrict__ e, const long long* __restrict__ pairs, int n) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        e[pairs[2 * k]].value = __longlong_as_double(pairs[2 * k + 1]);
 }
 
 __global__ void coo_finish_row_ptr_kernel(const long long* __restrict__ scan, long long total, int rows,

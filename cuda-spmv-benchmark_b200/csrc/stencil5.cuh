@@ -26,6 +26,7 @@
 // Arithmetic order is the reference's (read from its PTX): t = vC*xC; fma(vW,xW,t); fma(vE,xE,t);
 // fma(vN,xN,t); fma(vS,xS,t); boundary rows: fma chain over k from 0.0.
 #pragma once
+#include "cg_kernels.cuh"
 #include "common.cuh"
 
 namespace b200 {
@@ -43,7 +44,7 @@ struct Stencil5Args {
     double* y;                // PLAIN/DOT: A x ; RESID: r = b - A x
     double* y2;               // RESID: second copy (p = r)
     const double* b;          // RESID
-    double* partials;         // DOT/RESID: one double per CTA (gridDim.x entries)
+    double* partials;         // DOT/RESID/FUSED: one double per CTA (gridDim.x entries)
     long long base0;          // interior element (i,j) lives at base0 + i*row_stride + 5*j
     long long row_stride;
     long long row_offset;
@@ -66,6 +67,7 @@ struct Stencil5Args {
     const double* r;       // residual (local)
     double* xs;            // solution vector: xs += alpha * p_old
     const double* ab;      // device scalars: ab[0] = alpha (of the previous iteration), ab[1] = beta
+    const uint32_t* epoch_ptr;  // if set: the halo sequence number to wait for is read from here
 };
 
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, int* error_word) {
@@ -139,6 +141,9 @@ __device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long 
     return (MODE == ST_DOT) ? xc * sum : 0.0;
 }
 
+// registers: the fused mode sits at exactly 128 per thread with 4 columns per lane (4 CTAs of 4 warps per
+// SM); anything that adds live state to the row loop (a ticket per CTA, a second halo stream) drops it to
+// 3 CTAs per SM and costs ~10 % -- reductions and halo copies of the direction live in their own launches
 template <int MODE, int COLS, int WARPS, int STAGES, bool CG_LOADS>
 __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args a) {
     constexpr int W = 32 * COLS;                 // strip width in columns
@@ -146,18 +151,21 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double warp_part[WARPS];
 
+    if (MODE != ST_PLAIN) griddep_wait();  // programmatic dependent launch: nothing of the previous kernel is read above
     if (a.converged != nullptr && *a.converged != 0) return;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
     const double alpha = (MODE == ST_FUSED) ? a.ab[0] : 0.0, beta = (MODE == ST_FUSED) ? a.ab[1] : 0.0;
+    // the halo sequence number to wait for is only read where a wait happens (no live register elsewhere)
+    auto wanted = [&]() -> uint32_t { return (a.epoch_ptr != nullptr) ? __ldcg(a.epoch_ptr) : a.epoch; };
 
     if ((int)blockIdx.x >= a.n_interior_ctas) {
         // ------------------------------------------------------------ boundary pass (CSR walk)
         if (a.flag_prev != nullptr || a.flag_next != nullptr) {
             if (threadIdx.x == 0) {
-                if (a.flag_prev) wait_flag(a.flag_prev, a.epoch, a.error_word);
-                if (a.flag_next) wait_flag(a.flag_next, a.epoch, a.error_word);
+                if (a.flag_prev) wait_flag(a.flag_prev, wanted(), a.error_word);
+                if (a.flag_next) wait_flag(a.flag_next, wanted(), a.error_word);
             }
             __syncthreads();
         }
@@ -205,8 +213,8 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 const bool need_prev = ((long long)(i0 - 1) * n + j0 - 1 < off);
                 const bool need_next = ((long long)i1 * n + j0 + count + 1 > off + nl);
                 if (lane == 0) {
-                    if (need_prev && a.flag_prev) wait_flag(a.flag_prev, a.epoch, a.error_word);
-                    if (need_next && a.flag_next) wait_flag(a.flag_next, a.epoch, a.error_word);
+                    if (need_prev && a.flag_prev) wait_flag(a.flag_prev, wanted(), a.error_word);
+                    if (need_next && a.flag_next) wait_flag(a.flag_next, wanted(), a.error_word);
                 }
                 __syncwarp();
             }
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                     po = __ldg(a.x + idx);
                     return __ldg(a.r + idx);
                 }
-                return x_at<ST_PLAIN, CG_LOADS>(a, idx);
+                return x_at<ST_PLAIN, CG_LOADS>(a, idx);  // the halos already hold the NEW p
             };
             auto load_row = [&](int ii, double (&xr)[COLS], double& er, double (&po)[COLS], double& pe) {
                 const long long rb = (long long)ii * n;
@@ -421,10 +429,14 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
         }
     }
 
+    if (MODE != ST_PLAIN) griddep_launch();
     if (MODE != ST_PLAIN) {
         acc = warp_sum(acc);
         if (lane == 0) warp_part[warp] = acc;
         __syncthreads();
+        // One partial per CTA, fixed owner.  The grid has O(1e5) short-lived CTAs: a ticket per CTA (fence +
+        // atomic round trip, ~1 us of a ~30 us CTA) cost 3 % of the kernel, so the fixed-order final sum runs
+        // in cg_reduce_kernel instead, launched programmatically behind this grid (no launch gap).
         if (threadIdx.x == 0) {
             double t = 0.0;
 #pragma unroll

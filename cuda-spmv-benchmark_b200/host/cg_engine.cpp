@@ -14,13 +14,23 @@
 // that waits on a peer flag is always enqueued after the kernel that sets it: with virtual ranks on
 // one stream the waits are satisfied on arrival, with real GPUs they overlap.
 //
-// The host never blocks inside the iteration loop: the convergence test lives in the reduce
-// kernel, later kernels turn into no-ops once it fires, and the host polls a pinned status word
-// kLag iterations behind (the reference does a blocking 4-byte D2H every iteration,
+// The host never blocks inside the iteration loop: the convergence test lives in the tail of the
+// kernel that produces r.r, later kernels turn into no-ops once it fires, and the host polls a pinned
+// status word kLag iterations behind (the reference does a blocking 4-byte D2H every iteration,
 // cg_solver.cu:598-599).
+//
+// Every local rank is driven by its own host thread (one enqueue thread per GPU when one process
+// drives several devices, the north-star topology).  Exchange sequence numbers are counted on the
+// device, so the threads -- or processes -- need not agree on how many no-op iterations they enqueue
+// behind the convergence point.  Ranks that share one device and one stream (virtual ranks, tests)
+// run in lockstep instead: a phase barrier between the threads keeps every kernel that waits on a
+// peer behind the kernels that feed it.
 #include <math.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -62,8 +72,7 @@ struct Mgpu {
     bool opened[kMaxRanks];  // mapped through cudaIpcOpenMemHandle
     size_t halo_cap = 0;     // doubles per landing buffer
     size_t area_bytes = 0;   // offset of the first landing buffer inside a block
-    uint32_t halo_epoch = 0, red_epoch = 0;
-    bool single_device = true;  // all local ranks on one device: split reduce launches
+    bool single_device = true;  // all local ranks on one device and one stream: lockstep + split reductions
 } g;
 
 // block = exchange area | landing_prev | landing_next (written by the neighbours) | 4 local buffers:
@@ -74,6 +83,7 @@ double* landing_next(int r) { return landing_prev(r) + g.halo_cap; }
 double* halo_dir(int r, int parity, int next) { return landing_prev(r) + (2 + 2 * (parity & 1) + (next ? 1 : 0)) * g.halo_cap; }
 uint32_t* flag_prev(int r) { return reinterpret_cast<uint32_t*>(static_cast<char*>(g.xchg[r]) + b200_xchg_flag_prev_offset()); }
 uint32_t* flag_next(int r) { return reinterpret_cast<uint32_t*>(static_cast<char*>(g.xchg[r]) + b200_xchg_flag_next_offset()); }
+const uint32_t* halo_seq(int r) { return reinterpret_cast<const uint32_t*>(static_cast<char*>(g.xchg[r]) + b200_xchg_halo_seq_offset()); }
 
 void mgpu_reset() {
     if (!g.inited) return;
@@ -180,30 +190,31 @@ struct RankWs {
     DeviceBand band;
     bool own_band = false;
     double *x = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *Ap = nullptr, *b = nullptr;
-    double *partials = nullptr, *partials2 = nullptr, *stash = nullptr, *sums = nullptr;
+    // reduction context: per-CTA partials (two sums), group sums, tickets, local totals, results
+    double *partials = nullptr, *partials2 = nullptr, *gsum = nullptr, *stash = nullptr, *sums = nullptr;
+    uint32_t* tickets = nullptr;
     double* dinv = nullptr;  // Jacobi PCG: 1 / diag(A), allocated on first use
     int* dinv_err = nullptr;
     void* scalars = nullptr;
     HostStatus* status = nullptr;  // pinned + mapped
     void* status_dev = nullptr;
-    void** peer_table_host = nullptr;
-    int max_partials = 0;
+    long long max_partials = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<cudaEvent_t> iter_ev;
     std::vector<cudaEvent_t> phase_ev;  // detailed timers
 
     void free_vectors() {
         cudaFree(x); cudaFree(r); cudaFree(p); cudaFree(p2); cudaFree(Ap); cudaFree(b);
-        cudaFree(partials); cudaFree(partials2); cudaFree(stash); cudaFree(sums); cudaFree(scalars);
+        cudaFree(partials); cudaFree(partials2); cudaFree(gsum); cudaFree(tickets); cudaFree(stash); cudaFree(sums);
+        cudaFree(scalars);
         cudaFree(dinv); cudaFree(dinv_err);
         dinv = nullptr; dinv_err = nullptr;
-        x = r = p = p2 = Ap = b = partials = partials2 = stash = sums = nullptr;
+        x = r = p = p2 = Ap = b = partials = partials2 = gsum = stash = sums = nullptr;
+        tickets = nullptr;
         scalars = nullptr;
         if (status) cudaFreeHost((void*)status);
         status = nullptr;
-        for (auto e : iter_ev) cudaEventDestroy(e);
         for (auto e : phase_ev) cudaEventDestroy(e);
-        iter_ev.clear(); phase_ev.clear();
+        phase_ev.clear();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         ev0 = ev1 = nullptr;
@@ -228,7 +239,7 @@ struct Workspace {
     }
 } ws;
 
-int alloc_rank_vectors(RankWs& w, int max_partials) {
+int alloc_rank_vectors(RankWs& w, long long max_partials) {
     B200_CUDA(cudaSetDevice(w.dev));
     const size_t vb = (size_t)w.nl * sizeof(double);
     B200_CUDA(cudaMalloc(&w.x, vb));
@@ -238,8 +249,12 @@ int alloc_rank_vectors(RankWs& w, int max_partials) {
     B200_CUDA(cudaMalloc(&w.Ap, vb));
     B200_CUDA(cudaMalloc(&w.b, vb));
     w.max_partials = max_partials;
+    const size_t groups = (size_t)((max_partials + 255) / 256);
     B200_CUDA(cudaMalloc(&w.partials, (size_t)max_partials * sizeof(double)));
     B200_CUDA(cudaMalloc(&w.partials2, (size_t)max_partials * sizeof(double)));
+    B200_CUDA(cudaMalloc(&w.gsum, 2 * groups * sizeof(double)));
+    B200_CUDA(cudaMalloc(&w.tickets, (groups + 1) * sizeof(uint32_t)));
+    B200_CUDA(cudaMemset(w.tickets, 0, (groups + 1) * sizeof(uint32_t)));  // once: the counters reset themselves
     B200_CUDA(cudaMalloc(&w.stash, 4 * sizeof(double)));
     B200_CUDA(cudaMalloc(&w.sums, 4 * sizeof(double)));
     B200_CUDA(cudaMalloc(&w.scalars, b200_cg_scalars_bytes()));
@@ -250,21 +265,13 @@ int alloc_rank_vectors(RankWs& w, int max_partials) {
     return 0;
 }
 
-cudaEvent_t iter_event(RankWs& w, int k) {
-    while ((int)w.iter_ev.size() <= k) {
-        cudaEvent_t e;
-        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        w.iter_ev.push_back(e);
-    }
-    return w.iter_ev[k];
-}
-
 struct PhaseTimer {  // detailed timers on the first local rank only (enable_detailed_timers)
     RankWs* w = nullptr;
     bool on = false;
     size_t used = 0;
     std::vector<int> tags;
-    void mark(int tag) {
+    std::vector<int> iter;  // iteration the mark belongs to (-1: outside the loop)
+    void mark(int tag, int it = -1) {
         if (!on) return;
         if (used == w->phase_ev.size()) {
             cudaEvent_t e;
@@ -273,6 +280,7 @@ struct PhaseTimer {  // detailed timers on the first local rank only (enable_det
         }
         cudaEventRecord(w->phase_ev[used++], w->st);
         tags.push_back(tag);
+        iter.push_back(it);
     }
 };
 enum { T_BEGIN = 0, T_SPMV, T_RED_PAP, T_XR, T_RED_RR, T_P, T_HALO, T_INIT_R, T_RED_RR0, T_N };
@@ -282,30 +290,14 @@ struct SolveOut {
     double residual = 0, b_norm = 0, total_ms = 0, sum = 0, norm = 0;
     double phase_ms[T_N] = {0};
     int phase_cnt[T_N] = {0};
+    double tail_ms[8] = {0};  // device-measured reduction tails (final sum + rank exchange + scalars)
+    int tail_cnt[8] = {0};
+    double gap_ms[8] = {0};   // device-measured time between two tails = the kernels that fed the second one
+    bool have_events = false;
 };
 SolveOut g_last;  // per-phase event times of the most recent solve (enable_detailed_timers)
 
-// band descriptor of rank w with its halo wiring for this epoch
-void wire_band(const RankWs& w, b200_band* b, bool halos, uint32_t epoch) {
-    w.band.describe(b);
-    if (halos && g.world > 1) {
-        if (w.rank > 0) { b->d_halo_prev = landing_prev(w.rank); b->d_flag_prev = flag_prev(w.rank); }
-        if (w.rank < g.world - 1) { b->d_halo_next = landing_next(w.rank); b->d_flag_next = flag_next(w.rank); }
-        b->epoch = epoch;
-    }
-}
-
-// band descriptor whose halos are the local direction copies of the given parity (no flags: the
-// halo-direction kernel has already waited for the neighbours)
-void wire_band_dir(const RankWs& w, b200_band* b, int parity) {
-    w.band.describe(b);
-    if (g.world > 1) {
-        if (w.rank > 0) b->d_halo_prev = halo_dir(w.rank, parity, 0);
-        if (w.rank < g.world - 1) b->d_halo_next = halo_dir(w.rank, parity, 1);
-    }
-}
-
-// deferred-x schedule (4 launches, 112 B/row per iteration) unless B200_CG_SCHEDULE=classic or
+// deferred-x schedule (2 launches, 112 B/row per iteration) unless B200_CG_SCHEDULE=classic or
 // b200_cg_set_schedule(0)
 int g_schedule = -1;
 bool schedule_deferred_x() {
@@ -316,14 +308,86 @@ bool schedule_deferred_x() {
     return g_schedule == 1;
 }
 
-int push_halo(const RankWs& w, const double* v, uint32_t epoch, const void* scalars) {
-    const int n = ws.grid;
-    double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;  // I am the "next" neighbour of rank-1
-    double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
-    uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
-    uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
-    return b200_halo_push(v, w.nl, n, dprev, dnext, fprev, fnext, epoch, g.xchg[w.rank], scalars, w.st);
+// where rank w's edges go and which words announce them
+b200_halo_push_args push_args(const RankWs& w) {
+    b200_halo_push_args h;
+    memset(&h, 0, sizeof h);
+    h.d_dst_prev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;  // I am the "next" neighbour of rank-1
+    h.d_dst_next = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
+    h.d_flag_prev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
+    h.d_flag_next = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
+    h.d_my_xchg = g.xchg[w.rank];
+    h.halo = ws.grid;
+    return h;
 }
+
+// band descriptor of rank w reading its halos from the landing buffers the neighbours push into;
+// rows that touch a halo wait for the neighbours' arrival words to reach this rank's own halo
+// sequence number (device-side: every rank pushes in the same phases)
+void wire_band(const RankWs& w, b200_band* b) {
+    w.band.describe(b);
+    if (g.world > 1) {
+        if (w.rank > 0) { b->d_halo_prev = landing_prev(w.rank); b->d_flag_prev = flag_prev(w.rank); }
+        if (w.rank < g.world - 1) { b->d_halo_next = landing_next(w.rank); b->d_flag_next = flag_next(w.rank); }
+        b->d_epoch_ptr = halo_seq(w.rank);
+    }
+}
+
+// band descriptor whose halos are the local direction copies of the given parity (no flags: the
+// kernel that wrote them has already waited for the neighbours)
+void wire_band_dir(const RankWs& w, b200_band* b, int parity) {
+    w.band.describe(b);
+    if (g.world > 1) {
+        if (w.rank > 0) b->d_halo_prev = halo_dir(w.rank, parity, 0);
+        if (w.rank < g.world - 1) b->d_halo_next = halo_dir(w.rank, parity, 1);
+    }
+}
+
+// The local ranks of one solve.  lockstep: they share a device and a stream, so every kernel that
+// waits on a peer must be enqueued after the kernels that feed it -- phase() is a barrier between
+// the rank threads.  Real GPUs: phase() is free, every thread runs ahead on its own.
+class Team {
+   public:
+    Team(int n, bool lockstep) : n_(n), lockstep_(lockstep && n > 1) {}
+    bool lockstep() const { return lockstep_; }
+    bool phase() {
+        if (!lockstep_) return !aborted_;
+        std::unique_lock<std::mutex> lk(m_);
+        if (aborted_) return false;
+        const unsigned gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            gen_++;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != gen || aborted_; });
+        }
+        return !aborted_;
+    }
+    // decision taken by the leader for everybody (lockstep) or by every rank for itself
+    bool agree(bool mine, bool leader) {
+        if (!lockstep_) return mine;
+        if (leader) shared_ = mine;
+        if (!phase()) return true;
+        const bool v = shared_;
+        if (!phase()) return true;
+        return v;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(m_);
+        aborted_ = true;
+        cv_.notify_all();
+    }
+   private:
+    int n_;
+    bool lockstep_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    int count_ = 0;
+    unsigned gen_ = 0;
+    bool aborted_ = false;
+    volatile bool shared_ = false;
+};
 
 }  // namespace
 
@@ -331,57 +395,60 @@ namespace {
 
 struct Engine {
     bool fused;           // band kernels available (stencil operators / mgpu); else op->run_device
-    bool pcg = false;     // Jacobi-preconditioned CG (single GPU, classic launch grouping)
+    bool pcg = false;     // Jacobi-preconditioned CG (classic launch grouping)
     SpmvOperator* op;     // generic path
-    int n_partials_spmv[kMaxRanks];
 
-    // dir_it >= 0 (multi-GPU deferred-x schedule, which == 2): the reduce CTA also advances the halo
-    // copies of the direction from parity dir_it to dir_it + 1
-    int for_ranks_reduce(int which, double tol, const int* n_partials, bool second_buf, uint32_t epoch, int dir_it = -1) {
-        const int phases_list_fused[1] = {3};
-        const int phases_list_split[2] = {1, 2};
-        const bool split = (g.world > 1 && g.single_device && ws.ranks.size() > 1);
-        const int* pl = split ? phases_list_split : phases_list_fused;
-        const int np = split ? 2 : 1;
-        for (int pi = 0; pi < np; pi++) {
-            for (size_t l = 0; l < ws.ranks.size(); l++) {
-                RankWs& w = ws.ranks[l];
-                B200_CUDA(cudaSetDevice(w.dev));
-                if (dir_it >= 0 && which == 2 && g.world > 1) {
-                    B200_K(b200_cg_reduce_rr_dir(second_buf ? w.partials2 : w.partials, n_partials[l], pl[pi], tol, w.scalars,
-                                                 w.status_dev, w.rank, g.world, epoch, g.xchg, w.stash,
-                                                 w.rank > 0 ? landing_prev(w.rank) : nullptr,
-                                                 w.rank < g.world - 1 ? landing_next(w.rank) : nullptr,
-                                                 halo_dir(w.rank, dir_it, 0), halo_dir(w.rank, dir_it, 1),
-                                                 halo_dir(w.rank, dir_it + 1, 0), halo_dir(w.rank, dir_it + 1, 1), ws.grid,
-                                                 flag_prev(w.rank), flag_next(w.rank), g.halo_epoch, w.st));
-                    continue;
-                }
-                B200_K(b200_cg_reduce(second_buf ? w.partials2 : w.partials, n_partials[l], which, pl[pi], tol,
-                                      w.scalars, which == 3 ? nullptr : w.status_dev, w.sums, w.rank, g.world, epoch,
-                                      g.world > 1 ? g.xchg : nullptr, w.stash, w.st));
-            }
-        }
-        return 0;
+    // per-solve parameters shared by the rank threads
+    const double* b_host = nullptr;
+    double* x_host = nullptr;
+    int max_iters = 0, verbose = 0, timers = 0;
+    double tol = 0;
+    const char* tag = "";
+    PhaseTimer pt;
+    double rank_ms[kMaxRanks] = {0};
+    double sums[2] = {0, 0};
+
+    b200_reduce_ctx ctx_of(const RankWs& w, int phases) const {
+        b200_reduce_ctx c;
+        memset(&c, 0, sizeof c);
+        c.d_scalars = w.scalars; c.h_status_mapped = w.status_dev;
+        c.d_partials = w.partials; c.d_partials_b = w.partials2;
+        c.d_group_sums = w.gsum; c.d_tickets = w.tickets; c.capacity = w.max_partials;
+        c.d_stash = w.stash; c.d_out = w.sums;
+        c.rank = w.rank; c.world = g.world;
+        c.d_peer_xchg = g.world > 1 ? g.xchg : nullptr;
+        c.tol = tol; c.phases = phases;
+        return c;
     }
 
-    int solve(const double* b_host, double* x_host, int max_iters, double tol, int verbose, int timers,
-              const char* tag, SolveOut* out) {
-        const size_t L = ws.ranks.size();
+    // One rank, start to finish.  `tail`: 3 = every reduction completes inside its producing kernel;
+    // 1 (lockstep) = the producer sums and stores to the peers, the wait half follows as its own
+    // launch once every rank's producer is in the stream.
+    int solve_rank(size_t l, Team& team) {
+        RankWs& w = ws.ranks[l];
         const bool multi = g.world > 1;
+        const bool lead = (l == 0);
+        const int tail = team.lockstep() ? 1 : 3;
+        B200_CUDA(cudaSetDevice(w.dev));
+        const b200_reduce_ctx ctx = ctx_of(w, tail);
+        // second half of a split reduction
+        auto combine = [&](int which, int two) -> int {
+            if (!team.lockstep()) return 0;
+            if (!team.phase()) return 1;
+            B200_K(b200_cg_reduce(&ctx, which, 0, two, 2, w.st));
+            return 0;
+        };
+        auto mark = [&](int t, int it = -1) { if (lead) pt.mark(t, it); };
+        const b200_halo_push_args push = multi ? push_args(w) : b200_halo_push_args();
+
         // ---- untimed: upload b and the initial guess (reference cg_solver.cu:473-474)
-        for (auto& w : ws.ranks) {
-            B200_CUDA(cudaSetDevice(w.dev));
-            B200_CUDA(cudaMemsetAsync(w.scalars, 0, b200_cg_scalars_bytes(), w.st));
-            memset((void*)w.status, 0, sizeof(HostStatus));
-            B200_CUDA(cudaMemcpyAsync(w.b, b_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
-            B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
-        }
+        B200_CUDA(cudaMemsetAsync(w.scalars, 0, b200_cg_scalars_bytes(), w.st));
+        memset((void*)w.status, 0, sizeof(HostStatus));
+        B200_CUDA(cudaMemcpyAsync(w.b, b_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
+        B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
         if (pcg) {
             // untimed set-up like the uploads: dinv = 1 / diag(A), rebuilt for every solve (the matrix
             // behind an operator may have changed while the shape stayed the same)
-            if (multi) { fprintf(stderr, "[ERROR] Jacobi PCG is single-GPU\n"); return 1; }
-            RankWs& w = ws.ranks[0];
             int ell_width = 0;
             const DeviceBand* m = fused ? &w.band : operator_matrix(op, &ell_width);
             if (!m) { fprintf(stderr, "[ERROR] Jacobi PCG needs one of this library's operators (diagonal access)\n"); return 1; }
@@ -398,267 +465,231 @@ struct Engine {
             B200_CUDA(cudaStreamSynchronize(w.st));
             if (bad) { fprintf(stderr, "[ERROR] Jacobi PCG: a row has no (or a zero) diagonal entry\n"); return 1; }
         }
-        for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
+        B200_CUDA(cudaStreamSynchronize(w.st));
         if (multi) {
             // Align the ranks before the clock starts (the reference does MPI_Barrier right before its
-            // start event, cg_solver_mgpu_partitioned.cu:405-413): an empty rank-exchange reduction is
-            // a device-side barrier over peer memory.  Without it a rank whose upload finished early
+            // start event, cg_solver_mgpu_partitioned.cu:405-413): an empty rank exchange is a
+            // device-side barrier over peer memory.  Without it a rank whose upload finished early
             // would count its neighbours' PCIe time as solver time.
-            int zero[kMaxRanks] = {0};
-            if (for_ranks_reduce(3, tol, zero, false, ++g.red_epoch)) return 1;
-            for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
+            if (!team.phase()) return 1;
+            B200_K(b200_cg_reduce(&ctx, B200_RED_SUM, 0, 0, tail, w.st));
+            if (combine(B200_RED_SUM, 0)) return 1;
+            B200_CUDA(cudaStreamSynchronize(w.st));
         }
+        if (!team.phase()) return 1;
+        B200_CUDA(cudaEventRecord(w.ev0, w.st));
+        mark(T_BEGIN);
 
-        PhaseTimer pt;
-        pt.w = &ws.ranks[0];
-        pt.on = timers != 0;
-        for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaEventRecord(w.ev0, w.st)); }
-        B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-        pt.mark(T_BEGIN);
-
-        int np[kMaxRanks];
         // ---- setup: r = b - A x0, p = r, rr_old = r.r, b_norm = sqrt(rr_old)   (cg_solver.cu:498-528)
         if (multi) {
-            const uint32_t e = ++g.halo_epoch;
-            for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_K(push_halo(w, w.x, e, nullptr)); }
+            B200_K(b200_halo_push(w.x, w.nl, &push, nullptr, w.st));
+            if (!team.phase()) return 1;
         }
-        for (size_t l = 0; l < L; l++) {
-            RankWs& w = ws.ranks[l];
-            B200_CUDA(cudaSetDevice(w.dev));
-            if (fused) {
-                b200_band band;
-                wire_band(w, &band, true, g.halo_epoch);
-                B200_K(b200_cg_residual_init(&band, w.x, w.b, w.r, w.p, w.partials, w.scalars, w.st));
-                np[l] = n_partials_spmv[l];
-            } else {
-                if (op->run_device(w.x, w.Ap) != 0) return 1;
-                B200_K(b200_residual_init_generic(w.nl, w.b, w.Ap, w.r, w.p, w.partials, &np[l], w.st));
-            }
+        if (fused) {
+            b200_band band;
+            wire_band(w, &band);
+            B200_K(b200_cg_residual_init(&band, w.x, w.b, w.r, w.p, &ctx, w.st));
+        } else {
+            if (op->run_device(w.x, w.Ap) != 0) return 1;
+            B200_K(b200_residual_init_generic(w.nl, w.b, w.Ap, w.r, w.p, &ctx, w.st));
         }
-        B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-        pt.mark(T_INIT_R);
-        if (for_ranks_reduce(0, tol, np, false, ++g.red_epoch)) return 1;
-        B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-        pt.mark(T_RED_RR0);
+        mark(T_INIT_R);
+        if (combine(B200_RED_RR0, 0)) return 1;
+        if (team.lockstep()) mark(T_RED_RR0);
         if (pcg) {  // p0 = z0 = D^-1 r0, rho_0 = r0.z0
-            RankWs& w = ws.ranks[0];
-            B200_K(b200_pcg_init(w.nl, w.r, w.dinv, w.p, w.partials, &np[0], w.st));
-            if (for_ranks_reduce(4, tol, np, false, ++g.red_epoch)) return 1;
+            B200_K(b200_pcg_init(w.nl, w.r, w.dinv, w.p, &ctx, w.st));
+            if (combine(B200_RED_RZ0, 0)) return 1;
         }
-        if (multi) {
-            const uint32_t e = ++g.halo_epoch;
-            for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_K(push_halo(w, w.p, e, nullptr)); }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_HALO);
-        }
-        if (verbose >= 1) {
-            RankWs& w0 = ws.ranks[0];
-            B200_CUDA(cudaSetDevice(w0.dev));
-            B200_CUDA(cudaStreamSynchronize(w0.st));
-            printf("[%s] Initial residual: %e\n", tag, (double)w0.status->b_norm);
-        }
-
-        // ---- iterations (cg_solver.cu:538-638)
-        const int lag = verbose >= 2 ? 0 : kLag;
         const bool dx = fused && schedule_deferred_x() && !pcg;
-        if (multi && dx) {
-            // first direction: p0 = r0, its edges are in the landing buffers (pushed above)
-            for (auto& w : ws.ranks) {
-                B200_CUDA(cudaSetDevice(w.dev));
+        if (multi) {
+            B200_K(b200_halo_push(w.p, w.nl, &push, nullptr, w.st));
+            if (!team.phase()) return 1;
+            if (dx) {
+                // first direction: p0 = r0, its edges are in the landing buffers (pushed above)
                 B200_K(b200_cg_halo_dir(w.rank > 0 ? landing_prev(w.rank) : nullptr,
                                         w.rank < g.world - 1 ? landing_next(w.rank) : nullptr, nullptr, nullptr,
                                         halo_dir(w.rank, 0, 0), halo_dir(w.rank, 0, 1), ws.grid, flag_prev(w.rank),
-                                        flag_next(w.rank), g.halo_epoch, w.scalars, 1, w.st));
+                                        flag_next(w.rank), g.xchg[w.rank], w.scalars, 1, w.st));
             }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_HALO);
+            mark(T_HALO);
         }
-        const size_t loop_mark0 = pt.used;            // first phase mark of the iteration loop
-        // classic: K1, R, K2, R, K3 (halo push fused into K3); deferred x: K1F, R, K2r, R (+ halo direction)
-        const size_t marks_per_iter = dx ? 4 : 5;
-        int launched = 0;
+        if (verbose >= 1 && lead) {
+            B200_CUDA(cudaStreamSynchronize(w.st));
+            printf("[%s] Initial residual: %e\n", tag, (double)w.status->b_norm);
+        }
+
+        // ---- iterations (cg_solver.cu:538-638)
+        // classic: K1, K2, K3 (+ halo push); deferred x: K1F, K2r (+ r-edge push)
+        const int lag = verbose >= 2 ? 0 : kLag;
         bool done = false;
         Nvtx range_solver("CG_Solver");
         for (int it = 0; it < max_iters && !done; it++) {
             Nvtx range_iter("CG_Iteration");
             nvtxRangePushA("SpMV");
-            for (size_t l = 0; l < L; l++) {  // K1: Ap = A p, partials p.Ap
-                RankWs& w = ws.ranks[l];
-                B200_CUDA(cudaSetDevice(w.dev));
-                if (dx) {
-                    // direction k lives in p (k even) or p2 (k odd)
-                    double* pcur = (it & 1) ? w.p2 : w.p;
-                    double* pold = (it & 1) ? w.p : w.p2;
-                    b200_band band;
-                    wire_band_dir(w, &band, it);
-                    if (it == 0) B200_K(b200_cg_spmv_dot(&band, pcur, w.Ap, w.partials, w.scalars, w.st));
-                    else B200_K(b200_cg_spmv_fused(&band, pold, w.r, pcur, w.x, w.Ap, w.partials, w.scalars, w.st));
-                    np[l] = n_partials_spmv[l];
-                } else if (fused) {
-                    b200_band band;
-                    wire_band(w, &band, true, g.halo_epoch);
-                    B200_K(b200_cg_spmv_dot(&band, w.p, w.Ap, w.partials, w.scalars, w.st));
-                    np[l] = n_partials_spmv[l];
-                } else if (operator_spmv_dot(op, w.p, w.Ap, w.partials, w.max_partials, &np[l], w.scalars) != 0) {
+            if (dx) {
+                // direction k lives in p (k even) or p2 (k odd)
+                double* pcur = (it & 1) ? w.p2 : w.p;
+                double* pold = (it & 1) ? w.p : w.p2;
+                b200_band band;
+                wire_band_dir(w, &band, it);  // halo copies of direction `it` (kept by b200_cg_halo_dir)
+                if (it == 0) B200_K(b200_cg_spmv_dot(&band, pcur, w.Ap, &ctx, w.st));
+                else B200_K(b200_cg_spmv_fused(&band, pold, w.r, pcur, w.x, w.Ap, &ctx, w.st));
+            } else if (fused) {
+                b200_band band;
+                wire_band(w, &band);
+                B200_K(b200_cg_spmv_dot(&band, w.p, w.Ap, &ctx, w.st));
+            } else {
+                int np = 0;
+                if (operator_spmv_dot(op, w.p, w.Ap, w.partials, w.max_partials, &np, w.scalars) == 0) {
+                    // this library's generic CSR / ELLPACK kernels write one partial per warp item
+                    B200_K(b200_cg_reduce(&ctx, B200_RED_PAP, np, 0, 3, w.st));
+                } else {
                     // foreign operator (or unaligned arrays): SpMV through the vtable, then the dot pass
                     if (op->run_device(w.p, w.Ap) != 0) return 1;
-                    B200_K(b200_dot_partials(w.nl, w.scalars, w.Ap, w.p, w.partials, &np[l], w.st));
+                    B200_K(b200_dot_partials(w.nl, w.Ap, w.p, &ctx, w.st));
                 }
             }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_SPMV);
+            mark(T_SPMV, it);
             nvtxRangePop();
-            nvtxRangePushA("Dot_Product");
-            if (for_ranks_reduce(1, tol, np, false, ++g.red_epoch)) return 1;  // alpha
-            nvtxRangePop();
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_RED_PAP);
+            if (team.lockstep()) {
+                Nvtx range_dot("Dot_Product");
+                if (combine(B200_RED_PAP, 0)) return 1;
+                mark(T_RED_PAP, it);
+            }
             nvtxRangePushA("BLAS_AXPY");
             if (dx) {
-                // K2r: r -= alpha Ap, partials r.r; multi-GPU: the edges of the new r go straight into
-                // the neighbours' landing buffers, the last CTA publishes the arrival epoch
-                const uint32_t e = multi ? ++g.halo_epoch : 0;
-                for (size_t l = 0; l < L; l++) {
-                    RankWs& w = ws.ranks[l];
-                    B200_CUDA(cudaSetDevice(w.dev));
-                    if (multi) {
-                        double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
-                        double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
-                        uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
-                        uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
-                        B200_K(b200_cg_update_r_push(w.nl, w.scalars, w.Ap, w.r, w.partials2, &np[l], ws.grid, dprev, dnext,
-                                                     fprev, fnext, e, g.xchg[w.rank], w.st));
-                    } else {
-                        B200_K(b200_cg_update_r(w.nl, w.scalars, w.Ap, w.r, w.partials2, &np[l], w.st));
-                    }
-                }
-            } else if (pcg) {  // K2p: + partials r.z with z = D^-1 r
-                RankWs& w = ws.ranks[0];
-                B200_K(b200_pcg_update_xr(w.nl, w.scalars, w.p, w.Ap, w.dinv, w.x, w.r, w.partials2, w.partials, &np[0], w.st));
-            } else {
-                for (size_t l = 0; l < L; l++) {  // K2: x += alpha p, r -= alpha Ap, partials r.r
-                    RankWs& w = ws.ranks[l];
-                    B200_CUDA(cudaSetDevice(w.dev));
-                    B200_K(b200_cg_update_xr(w.nl, w.scalars, w.p, w.Ap, w.x, w.r, w.partials2, &np[l], w.st));
-                }
+                // K2r: r -= alpha Ap, r.r -> convergence, beta; multi-GPU: the edges of the new r go straight
+                // into the neighbours' landing buffers
+                B200_K(b200_cg_update_r(w.nl, w.Ap, w.r, multi ? &push : nullptr, &ctx, w.st));
+            } else if (pcg) {  // K2p: + r.z with z = D^-1 r
+                B200_K(b200_pcg_update_xr(w.nl, w.p, w.Ap, w.dinv, w.x, w.r, &ctx, w.st));
+            } else {  // K2: x += alpha p, r -= alpha Ap, r.r
+                B200_K(b200_cg_update_xr(w.nl, w.p, w.Ap, w.x, w.r, &ctx, w.st));
             }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_XR);
+            mark(T_XR, it);
             nvtxRangePop();
-            nvtxRangePushA("Dot_Product");
-            // convergence, beta; multi-GPU deferred-x: + halo copies of the next direction,
-            // p_halo = r_halo + beta p_halo_old (the r edges were pushed by K2r above)
-            if (pcg) {
-                RankWs& w = ws.ranks[0];
-                B200_K(b200_pcg_reduce(w.partials2, w.partials, np[0], tol, w.scalars, w.status_dev, w.st));
-            } else if (for_ranks_reduce(2, tol, np, true, ++g.red_epoch, (dx && multi) ? it : -1)) return 1;
-            nvtxRangePop();
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_RED_RR);
+            if (team.lockstep()) {
+                Nvtx range_dot("Dot_Product");
+                if (combine(pcg ? B200_RED_PCG : B200_RED_RR, pcg ? 1 : 0)) return 1;
+                mark(T_RED_RR, it);
+            }
+            if (dx && multi) {
+                // halo copies of the next direction: p_halo = r_halo + beta p_halo_old (the r edges were pushed
+                // by K2r, beta comes out of its tail) -- 2 x grid elements, a few CTAs; keeping this out of
+                // the SpMV kernel keeps that kernel at 4 CTAs per SM
+                if (team.lockstep() && !team.phase()) return 1;
+                B200_K(b200_cg_halo_dir(w.rank > 0 ? landing_prev(w.rank) : nullptr,
+                                        w.rank < g.world - 1 ? landing_next(w.rank) : nullptr, halo_dir(w.rank, it, 0),
+                                        halo_dir(w.rank, it, 1), halo_dir(w.rank, it + 1, 0), halo_dir(w.rank, it + 1, 1),
+                                        ws.grid, flag_prev(w.rank), flag_next(w.rank), g.xchg[w.rank], w.scalars, 0, w.st));
+                mark(T_HALO, it);
+            }
             if (!dx) {
                 Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
-                if (pcg) {  // K3p: p = D^-1 r + beta p
-                    RankWs& w = ws.ranks[0];
-                    B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, w.st));
-                } else if (!multi) {
-                    for (auto& w : ws.ranks) {  // K3: p = r + beta p
-                        B200_CUDA(cudaSetDevice(w.dev));
-                        B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));
-                    }
-                } else {
-                    // K3 + halo push in one launch: the edge elements of the new p go straight into the
-                    // neighbours' landing buffers, the last CTA publishes the arrival epoch
-                    const uint32_t e = ++g.halo_epoch;
-                    for (auto& w : ws.ranks) {
-                        B200_CUDA(cudaSetDevice(w.dev));
-                        double* dprev = w.rank > 0 ? landing_next(w.rank - 1) : nullptr;
-                        double* dnext = w.rank < g.world - 1 ? landing_prev(w.rank + 1) : nullptr;
-                        uint32_t* fprev = w.rank > 0 ? flag_next(w.rank - 1) : nullptr;
-                        uint32_t* fnext = w.rank < g.world - 1 ? flag_prev(w.rank + 1) : nullptr;
-                        B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, ws.grid, dprev, dnext, fprev, fnext, e,
-                                                     g.xchg[w.rank], w.st));
+                if (pcg) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, multi ? &push : nullptr, w.st));  // K3p
+                else if (!multi) B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));                        // K3
+                else B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, &push, w.st));  // K3 + halo push
+                if (multi && !team.phase()) return 1;
+                mark(T_P, it);
+            }
+            // look at the iteration finished `lag` launches ago: the tail of K2 publishes the iteration
+            // count (last, behind a system fence) in pinned memory
+            bool stop = false;
+            if (it >= lag) {
+                const int want = it - lag + 1;
+                unsigned spins = 0;
+                while (w.status->iterations < want && !w.status->converged && !w.status->error) {
+                    if ((++spins & 0x3ff) == 0) {
+                        const cudaError_t q = cudaStreamQuery(w.st);
+                        if (q == cudaSuccess) break;  // stream drained: the count can no longer change
+                        if (q != cudaErrorNotReady) B200_CUDA(q);
+                        std::this_thread::yield();
                     }
                 }
-                B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-                pt.mark(T_P);
+                if (verbose >= 2 && lead)
+                    printf("[%s] Iter %3d: residual = %e (rel = %e)\n", tag, (int)w.status->iterations,
+                           (double)w.status->residual, (double)w.status->residual / (double)w.status->b_norm);
+                if (w.status->converged || w.status->error) stop = true;
             }
-            RankWs& w0 = ws.ranks[0];
-            B200_CUDA(cudaSetDevice(w0.dev));
-            B200_CUDA(cudaEventRecord(iter_event(w0, it), w0.st));
-            launched = it + 1;
-            if (it >= lag) {  // look at the iteration finished `lag` launches ago
-                B200_CUDA(cudaEventSynchronize(w0.iter_ev[it - lag]));
-                if (verbose >= 2)
-                    printf("[%s] Iter %3d: residual = %e (rel = %e)\n", tag, (int)w0.status->iterations,
-                           (double)w0.status->residual, (double)w0.status->residual / (double)w0.status->b_norm);
-                if (w0.status->converged || w0.status->error) done = true;
-            }
+            done = team.agree(stop, lead);
         }
-        const size_t loop_mark1 = pt.used;
         if (dx) {
             // the x update of the last completed iteration is still pending: x += alpha p_last
-            for (auto& w : ws.ranks) {
-                B200_CUDA(cudaSetDevice(w.dev));
-                B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, w.st));
-            }
-            B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
-            pt.mark(T_P);
+            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, w.st));
+            mark(T_P);
         }
-        (void)launched;
-        for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaEventRecord(w.ev1, w.st)); }
-        double total = 0.0;
-        for (auto& w : ws.ranks) {
-            B200_CUDA(cudaSetDevice(w.dev));
-            B200_CUDA(cudaEventSynchronize(w.ev1));
-            float ms = 0.f;
-            B200_CUDA(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
-            if (ms > total) total = ms;  // slowest rank, like the reference's MPI_Reduce(MAX) (:758-763)
+        B200_CUDA(cudaEventRecord(w.ev1, w.st));
+        B200_CUDA(cudaEventSynchronize(w.ev1));
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+        rank_ms[l] = ms;
+
+        // ---- solution back to the host + checksums (cg_solver.cu:645,658-665), sums on the device
+        B200_CUDA(cudaMemcpyAsync(x_host + w.off, w.x, (size_t)w.nl * sizeof(double), cudaMemcpyDeviceToHost, w.st));
+        B200_K(b200_checksum(w.nl, w.x, &ctx, w.st));
+        if (combine(B200_RED_SUM, 1)) return 1;
+        if (lead) B200_CUDA(cudaMemcpyAsync(sums, w.sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, w.st));
+        B200_CUDA(cudaStreamSynchronize(w.st));
+        return 0;
+    }
+
+    int solve(const double* b_host_, double* x_host_, int max_iters_, double tol_, int verbose_, int timers_,
+              const char* tag_, SolveOut* out) {
+        const size_t L = ws.ranks.size();
+        b_host = b_host_; x_host = x_host_; max_iters = max_iters_; tol = tol_; verbose = verbose_; timers = timers_; tag = tag_;
+        if (pcg && !fused && g.world > 1) { fprintf(stderr, "[ERROR] multi-GPU PCG runs on the band kernels\n"); return 1; }
+        pt = PhaseTimer();
+        pt.w = &ws.ranks[0];
+        pt.on = timers != 0;
+        Team team((int)L, g.world > 1 && g.single_device && L > 1);
+        int rcs[kMaxRanks] = {0};
+        if (L == 1) {
+            rcs[0] = solve_rank(0, team);
+        } else {
+            // one enqueue thread per local rank (one per GPU when this process drives several)
+            std::vector<std::thread> th;
+            for (size_t l = 0; l < L; l++)
+                th.emplace_back([&, l] {
+                    rcs[l] = solve_rank(l, team);
+                    if (rcs[l]) team.abort();
+                });
+            for (auto& t : th) t.join();
         }
         RankWs& w0 = ws.ranks[0];
-        if (w0.status->error) {
+        B200_CUDA(cudaSetDevice(w0.dev));
+        for (size_t l = 0; l < L; l++)
+            if (rcs[l]) return rcs[l];
+        b200_cg_tail_times tt;
+        B200_K(b200_cg_read_tail_times(w0.scalars, &tt, w0.st));
+        if (w0.status->error || tt.error) {
             fprintf(stderr, "[b200] peer exchange timed out\n");
             return B200_ETIMEOUT;
         }
+        double total = 0.0;
+        for (size_t l = 0; l < L; l++)
+            if (rank_ms[l] > total) total = rank_ms[l];  // slowest rank, like the reference's MPI_Reduce(MAX) (:758-763)
         out->total_ms = total;
         out->iterations = w0.status->iterations;
         out->residual = w0.status->residual;
         out->b_norm = w0.status->b_norm;
         out->converged = (out->residual / out->b_norm < tol) ? 1 : 0;  // recomputed on the host (cg_solver.cu:656)
+        for (int k = 0; k < 8; k++) {
+            out->tail_ms[k] = tt.ns[k] * 1e-6; out->tail_cnt[k] = (int)tt.count[k]; out->gap_ms[k] = tt.gap_ns[k] * 1e-6;
+        }
+        out->have_events = pt.on;
         if (pt.on) {
-            B200_CUDA(cudaSetDevice(w0.dev));
             for (size_t k = 1; k < pt.used; k++) {
                 // launches enqueued after convergence (the host polls kLag iterations behind) are
                 // no-ops on the device: keep them out of the per-phase times and launch counts
-                if (k >= loop_mark0 && k < loop_mark1 && (k - loop_mark0) / marks_per_iter >= (size_t)out->iterations) continue;
+                if (pt.iter[k] >= out->iterations) continue;
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, w0.phase_ev[k - 1], w0.phase_ev[k]);
                 out->phase_ms[pt.tags[k]] += ms;
                 out->phase_cnt[pt.tags[k]]++;
             }
         }
-
-        // ---- solution back to the host + checksums (cg_solver.cu:645,658-665), sums on the device
-        for (auto& w : ws.ranks) {
-            B200_CUDA(cudaSetDevice(w.dev));
-            B200_CUDA(cudaMemcpyAsync(x_host + w.off, w.x, (size_t)w.nl * sizeof(double), cudaMemcpyDeviceToHost, w.st));
-        }
-        int npc[kMaxRanks];
-        for (size_t l = 0; l < L; l++) {
-            RankWs& w = ws.ranks[l];
-            B200_CUDA(cudaSetDevice(w.dev));
-            B200_K(b200_checksum_partials(w.nl, w.x, w.partials, w.partials2, &npc[l], w.st));
-        }
-        double sums[2] = {0, 0};
-        for (int which_buf = 0; which_buf < 2; which_buf++) {
-            if (for_ranks_reduce(3, tol, npc, which_buf == 1, ++g.red_epoch)) return 1;
-            B200_CUDA(cudaSetDevice(w0.dev));
-            B200_CUDA(cudaMemcpyAsync(&sums[which_buf], w0.sums, sizeof(double), cudaMemcpyDeviceToHost, w0.st));
-            B200_CUDA(cudaStreamSynchronize(w0.st));
-        }
-        for (auto& w : ws.ranks) { B200_CUDA(cudaSetDevice(w.dev)); B200_CUDA(cudaStreamSynchronize(w.st)); }
         out->sum = sums[0];
         out->norm = sqrt(sums[1]);
-        B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
         return 0;
     }
 };
@@ -710,17 +741,17 @@ int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Eng
                 if (upload_band_csr(mat, w.off, w.nl, &w.band, w.st)) return 1;
                 w.own_band = true;
             }
-            int maxp = 148 * 8;
-            if (!(eng->fused || fused_from_op)) {
-                const long long k = b200_csr_dot_partials_capacity(w.nl);  // generic operators: fused SpMV + dot
-                if (k > maxp) maxp = (int)k;
-            }
+            long long maxp = 0;
             if (eng->fused || fused_from_op) {
                 b200_band band;
                 w.band.describe(&band);
-                const int k = b200_cg_max_partials(&band);
+                const int k = b200_cg_max_partials(&band);  // STENCIL5 grid (halo CTAs included) or the BLAS-1 grid
                 if (k < 0) { fprintf(stderr, "[b200] %s\n", b200_last_error()); return 1; }
                 maxp = k;
+            } else {
+                maxp = 148LL * 64;  // BLAS-1 grids on any SM count this library runs on
+                const long long k = b200_csr_dot_partials_capacity(w.nl);  // generic operators: fused SpMV + dot
+                if (k > maxp) maxp = k;
             }
             if (alloc_rank_vectors(w, maxp)) return 1;
         }
@@ -732,24 +763,36 @@ int prepare_workspace(MatrixData* mat, SpmvOperator* op, bool fused_from_op, Eng
             ws.ranks[l].band = *ob;  // current device arrays of the operator (never owned here)
             ws.ranks[l].own_band = false;
         }
-        if (eng->fused || fused_from_op) {
-            b200_band band;
-            ws.ranks[l].band.describe(&band);
-            eng->n_partials_spmv[l] = b200_stencil5_num_partials(&band);
-        }
     }
     return 0;
 }
+
+// device-measured time of the reduction tails that ran inside the SpMV / BLAS-1 kernels of the loop
+double tails_in_spmv(const SolveOut& o) { return o.tail_ms[B200_RED_PAP] + o.tail_ms[B200_RED_RR0]; }
+double tails_in_blas1(const SolveOut& o) { return o.tail_ms[B200_RED_RR] + o.tail_ms[B200_RED_PCG]; }
 
 void fill_stats(const SolveOut& o, CGStats* s) {
     s->iterations = o.iterations;
     s->residual_norm = o.residual;
     s->time_total_ms = o.total_ms;
-    // fused kernels: SpMV time includes the p.Ap partial sums, BLAS-1 time the r.r partial sums;
-    // "reductions" are the two final-sum launches per iteration
-    s->time_spmv_ms = o.phase_ms[T_SPMV] + o.phase_ms[T_INIT_R];
-    s->time_blas1_ms = o.phase_ms[T_XR] + o.phase_ms[T_P];
+    // The final sums, the scalar recurrences and (multi-GPU) the rank exchange run in the tail of the
+    // kernel that produces the partial sums.  "reductions" = those tails, timed on the device, plus
+    // the stand-alone reduce launches of the paths that still have them; SpMV / BLAS-1 = the event
+    // time of the kernels minus their tails (only known with enable_detailed_timers).
+    // Without the timers the same split comes from the device clock: time between the r.r tail and the
+    // p.Ap tail = SpMV (classic schedule: + K3, which has no tail of its own), time between the p.Ap tail
+    // and the r.r tail = BLAS-1.  Never zero, so the reference's gflops_spmv = flops / time_spmv_ms
+    // (cg_metrics.cu:68) stays finite.
+    if (o.have_events) {
+        const double t_spmv = o.phase_ms[T_SPMV] + o.phase_ms[T_INIT_R], t_blas = o.phase_ms[T_XR] + o.phase_ms[T_P];
+        s->time_spmv_ms = t_spmv > tails_in_spmv(o) ? t_spmv - tails_in_spmv(o) : t_spmv;
+        s->time_blas1_ms = t_blas > tails_in_blas1(o) ? t_blas - tails_in_blas1(o) : t_blas;
+    } else {
+        s->time_spmv_ms = o.gap_ms[B200_RED_PAP] + o.gap_ms[B200_RED_RR0];
+        s->time_blas1_ms = o.gap_ms[B200_RED_RR] + o.gap_ms[B200_RED_PCG];
+    }
     s->time_reductions_ms = o.phase_ms[T_RED_PAP] + o.phase_ms[T_RED_RR] + o.phase_ms[T_RED_RR0];
+    for (int k = 0; k < 8; k++) s->time_reductions_ms += (k == B200_RED_SUM) ? 0.0 : o.tail_ms[k];
     s->converged = o.converged;
     s->solution_sum = o.sum;
     s->solution_norm = o.norm;
@@ -815,9 +858,21 @@ int cg_solve(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
     return solve_single(spmv_op, mat, b, x, config, stats, "CG");
 }
 
+namespace {
+int solve_mgpu(MatrixData* mat, const double* b, double* x, CGConfigMultiGPU config, CGStatsMultiGPU* stats, bool pcg);
+}
 int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
                               CGConfigMultiGPU config, CGStatsMultiGPU* stats) {
     (void)spmv_op;  // unused in the reference too (callers pass NULL)
+    return solve_mgpu(mat, b, x, config, stats, false);
+}
+int pcg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
+                               CGConfigMultiGPU config, CGStatsMultiGPU* stats) {
+    (void)spmv_op;
+    return solve_mgpu(mat, b, x, config, stats, true);
+}
+namespace {
+int solve_mgpu(MatrixData* mat, const double* b, double* x, CGConfigMultiGPU config, CGStatsMultiGPU* stats, bool pcg) {
     if (!mat || !b || !x || !stats) return 1;
     if (!g.inited) {  // default world: every visible GPU (override with B200_GPUS)
         int ndev = 0;
@@ -857,10 +912,11 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
     Engine eng;
     eng.op = nullptr;
     eng.fused = true;
+    eng.pcg = pcg;
     if (prepare_workspace(mat, nullptr, false, &eng)) return 1;
     SolveOut o;
     int rc = eng.solve(b, x, config.max_iters, config.tolerance, config.verbose, config.enable_detailed_timers,
-                       "CG-MGPU", &o);
+                       pcg ? "PCG-MGPU" : "CG-MGPU", &o);
     if (rc) return rc;
     g_last = o;
     memset(stats, 0, sizeof *stats);
@@ -870,15 +926,21 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
     stats->converged = o.converged;
     stats->solution_sum = o.sum;
     stats->solution_norm = o.norm;
-    stats->time_spmv_ms = o.phase_ms[T_SPMV];
-    stats->time_blas1_ms = o.phase_ms[T_XR] + o.phase_ms[T_P];
-    stats->time_reductions_ms = o.phase_ms[T_RED_PAP] + o.phase_ms[T_RED_RR] + o.phase_ms[T_RED_RR0];
-    stats->time_allreduce_ms = 0.0;  // the rank exchange is inside the reduce kernels
+    {
+        CGStats cs;
+        fill_stats(o, &cs);
+        stats->time_spmv_ms = cs.time_spmv_ms;
+        stats->time_blas1_ms = cs.time_blas1_ms;
+        stats->time_reductions_ms = cs.time_reductions_ms;
+    }
+    // the rank exchange (what the reference times as MPI_Allreduce) is part of the reduction tails
+    stats->time_allreduce_ms = 0.0;
     stats->time_allgather_ms = o.phase_ms[T_HALO];
     auto avg = [&](int t) { return o.phase_cnt[t] ? o.phase_ms[t] / o.phase_cnt[t] : 0.0; };
-    stats->time_dot_rs_initial_ms = o.phase_ms[T_RED_RR0];
-    stats->time_dot_pAp_ms = avg(T_RED_PAP);
-    stats->time_dot_rs_new_ms = avg(T_RED_RR);
+    auto tavg = [&](int k) { return o.tail_cnt[k] ? o.tail_ms[k] / o.tail_cnt[k] : 0.0; };
+    stats->time_dot_rs_initial_ms = o.phase_ms[T_RED_RR0] + o.tail_ms[B200_RED_RR0];
+    stats->time_dot_pAp_ms = avg(T_RED_PAP) + tavg(B200_RED_PAP);
+    stats->time_dot_rs_new_ms = avg(T_RED_RR) + tavg(B200_RED_RR) + tavg(B200_RED_PCG);
     stats->time_axpy_update_x_ms = avg(T_XR);  // x and r are updated by one fused kernel
     stats->time_axpy_update_r_ms = 0.0;
     stats->time_axpby_update_p_ms = avg(T_P);
@@ -890,6 +952,7 @@ int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const doub
     }
     return 0;
 }
+}  // namespace
 
 // Per-phase event times (ms) and launch counts of the most recent solve that ran with
 // enable_detailed_timers: [0] unused, [1] K1 SpMV+p.Ap, [2] reduce p.Ap, [3] K2 x/r update + r.r,
@@ -900,6 +963,56 @@ extern "C" int b200_last_phase_times(double* ms9, int* count9) {
         if (count9) count9[t] = g_last.phase_cnt[t];
     }
     return T_N;
+}
+
+// Device-measured reduction tails of the most recent solve (rank 0 of this process), indexed by the
+// B200_RED_* codes: total ms and number of tails.  A tail = fixed-order final sum + rank exchange over
+// peer memory (including the wait for the slowest rank) + scalar recurrence, inside the producing kernel.
+extern "C" int b200_last_tail_times(double* ms8, int* count8) {
+    for (int k = 0; k < 8; k++) {
+        if (ms8) ms8[k] = g_last.tail_ms[k];
+        if (count8) count8[k] = g_last.tail_cnt[k];
+    }
+    return 8;
+}
+
+// ... and the time between consecutive tails, attributed to the second one: the kernel(s) that produced its
+// partial sums (B200_RED_PAP: halo direction + SpMV; B200_RED_RR: K2 / K2r; classic schedule: K3 counts
+// towards the SpMV).  Device clock, recorded in every solve -- no events, so programmatic launches overlap.
+extern "C" int b200_last_gap_times(double* ms8) {
+    for (int k = 0; k < 8; k++)
+        if (ms8) ms8[k] = g_last.gap_ms[k];
+    return 8;
+}
+
+// Isolated cost of one halo exchange on the active multi-GPU world (after at least one solve): `reps`
+// back-to-back b200_halo_push launches of the direction vector's edges (grid doubles to each
+// neighbour, peer stores over NVLink + release of the arrival word), CUDA events around them.
+// In a solve this traffic rides inside K2r / K3; the probe is what bench.py reports against the
+// 900 GB/s per direction of NVLink 5.  Every rank must call it with the same `reps` (each push bumps
+// the device-side halo sequence number).  us_per_push = slowest local rank.
+extern "C" int b200_mgpu_halo_probe(int reps, double* us_per_push, long long* bytes_per_direction) {
+    if (!g.inited || g.world < 2 || ws.ranks.empty() || reps < 1 || !us_per_push) return 1;
+    double worst = 0.0;
+    for (auto& w : ws.ranks) {
+        B200_CUDA(cudaSetDevice(w.dev));
+        const b200_halo_push_args push = push_args(w);
+        B200_K(b200_halo_push(w.p, w.nl, &push, nullptr, w.st));  // warm-up
+        B200_CUDA(cudaEventRecord(w.ev0, w.st));
+        for (int k = 0; k < reps; k++) B200_K(b200_halo_push(w.p, w.nl, &push, nullptr, w.st));
+        B200_CUDA(cudaEventRecord(w.ev1, w.st));
+    }
+    for (auto& w : ws.ranks) {
+        B200_CUDA(cudaSetDevice(w.dev));
+        B200_CUDA(cudaEventSynchronize(w.ev1));
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, w.ev0, w.ev1));
+        if (ms * 1e3 / reps > worst) worst = ms * 1e3 / reps;
+    }
+    B200_CUDA(cudaSetDevice(ws.ranks[0].dev));
+    *us_per_push = worst;
+    if (bytes_per_direction) *bytes_per_direction = 8LL * ws.grid;
+    return 0;
 }
 
 // Declared but never defined in the reference (cg_solver_mgpu.h:88-89, "full replication").

@@ -93,6 +93,10 @@ MatrixData b200_synthetic_stencil(int grid_size);
 int b200_set_tuning(int variant, int rows_per_item);
 void b200_get_tuning(int* variant, int* rows_per_item);
 int b200_last_phase_times(double* ms9, int* count9);
+int b200_last_tail_times(double* ms8, int* count8);
+int b200_last_gap_times(double* ms8);
+int b200_mgpu_halo_probe(int reps, double* us_per_push, long long* bytes_per_direction);
+
 // device-resident ingest: .mtx -> COO on the GPU -> operator (no host Entry[] / CSR)
 int b200_load_matrix_market_device(const char* filename, MatrixData* meta, void** d_entries_out);
 int b200_operator_init_device_coo(SpmvOperator* op, const MatrixData* meta, const void* d_entries);
@@ -100,4 +104,8 @@ int b200_operator_device_csr(SpmvOperator* op, const int** d_row_ptr, const int*
                              long long* nnz);
 void b200_free_device(void* d_ptr);
 int b200_copy_to_host(void* h_dst, const void* d_src, size_t bytes);
+// pinned host buffers on the GPU's own NUMA node (host/host_alloc.cpp)
+int b200_host_node_of_device(int device);
+int b200_host_alloc_near(int device, size_t bytes, void** out, int* node_out);
+void b200_host_free(void* p);
 }

@@ -8,6 +8,33 @@
 
 #include "host_common.h"
 
+namespace {
+// owners: every early return of the loader releases what it holds
+struct PinnedText {
+    char* p = nullptr;
+    ~PinnedText() { if (p) cudaFreeHost(p); }
+};
+struct DeviceMem {
+    void* p = nullptr;
+    ~DeviceMem() { if (p) cudaFree(p); }
+    void* release() { void* q = p; p = nullptr; return q; }
+};
+
+int upload_host_entries(const char* filename, MatrixData* meta, void** d_entries_out) {
+    MatrixData m;
+    if (load_matrix_market(filename, &m) != 0) return 4;
+    *meta = m;
+    meta->entries = nullptr;
+    DeviceMem d;
+    cudaError_t e = cudaMalloc(&d.p, (size_t)(m.nnz > 0 ? m.nnz : 1) * sizeof(Entry));
+    if (e == cudaSuccess) e = cudaMemcpy(d.p, m.entries, (size_t)m.nnz * sizeof(Entry), cudaMemcpyHostToDevice);
+    free(m.entries);
+    if (e != cudaSuccess) { fprintf(stderr, "[b200] CUDA error: %s (%s:%d)\n", cudaGetErrorString(e), __FILE__, __LINE__); return 2; }
+    *d_entries_out = d.release();
+    return 0;
+}
+}  // namespace
+
 extern "C" int b200_load_matrix_market_device(const char* filename, MatrixData* meta, void** d_entries_out) {
     if (!filename || !meta || !d_entries_out) return 1;
     *d_entries_out = nullptr;
@@ -17,8 +44,9 @@ extern "C" int b200_load_matrix_market_device(const char* filename, MatrixData* 
     fseek(f, 0, SEEK_END);
     const long long size = ftell(f);
     fseek(f, 0, SEEK_SET);
-    char* host = nullptr;
-    if (cudaHostAlloc((void**)&host, (size_t)size + 1, cudaHostAllocDefault) != cudaSuccess) { fclose(f); return 3; }
+    PinnedText text;
+    if (cudaHostAlloc((void**)&text.p, (size_t)size + 1, cudaHostAllocDefault) != cudaSuccess) { fclose(f); return 3; }
+    char* host = text.p;
     const size_t got = fread(host, 1, (size_t)size, f);
     fclose(f);
     host[got] = 0;
@@ -38,51 +66,34 @@ extern "C" int b200_load_matrix_market_device(const char* filename, MatrixData* 
         if (sscanf(line.c_str(), "%d %d %d", &meta->rows, &meta->cols, &meta->nnz) == 3) have_size = true;
         break;
     }
-    auto host_fallback = [&]() -> int {
-        cudaFreeHost(host);
-        MatrixData m;
-        if (load_matrix_market(filename, &m) != 0) return 4;
-        *meta = m;
-        meta->entries = nullptr;
-        void* d = nullptr;
-        B200_CUDA(cudaMalloc(&d, (size_t)(m.nnz > 0 ? m.nnz : 1) * sizeof(Entry)));
-        B200_CUDA(cudaMemcpy(d, m.entries, (size_t)m.nnz * sizeof(Entry), cudaMemcpyHostToDevice));
-        free(m.entries);
-        *d_entries_out = d;
-        return 0;
-    };
-    if (!have_size || meta->nnz < 0) { cudaFreeHost(host); fprintf(stderr, "Error reading matrix size line\n"); return 2; }
-    if (symmetric) return host_fallback();  // mirrored entries: host expansion, then upload
+    if (!have_size || meta->nnz < 0) { fprintf(stderr, "Error reading matrix size line\n"); return 2; }
+    if (symmetric) return upload_host_entries(filename, meta, d_entries_out);  // mirrored entries: host expansion, then upload
     const long long text_bytes = (long long)got - pos;
-    void* d_text = nullptr;
-    void* d_entries = nullptr;
-    B200_CUDA(cudaMalloc(&d_text, (size_t)(text_bytes > 0 ? text_bytes : 1)));
-    B200_CUDA(cudaMalloc(&d_entries, (size_t)(meta->nnz > 0 ? meta->nnz : 1) * sizeof(Entry)));
-    B200_CUDA(cudaMemcpy(d_text, host + pos, (size_t)(text_bytes > 0 ? text_bytes : 0), cudaMemcpyHostToDevice));
+    DeviceMem d_text, d_entries;
+    B200_CUDA(cudaMalloc(&d_text.p, (size_t)(text_bytes > 0 ? text_bytes : 1)));
+    B200_CUDA(cudaMalloc(&d_entries.p, (size_t)(meta->nnz > 0 ? meta->nnz : 1) * sizeof(Entry)));
+    B200_CUDA(cudaMemcpy(d_text.p, host + pos, (size_t)(text_bytes > 0 ? text_bytes : 0), cudaMemcpyHostToDevice));
     const int cap = 1 << 16;
     std::vector<long long> pairs((size_t)2 * cap);
     long long lines = 0;
     int inexact = 0, malformed = 0;
-    int rc = b200_parse_mtx_entries(d_text, text_bytes, meta->nnz, d_entries, &lines, &inexact, pairs.data(), cap,
+    int rc = b200_parse_mtx_entries(d_text.p, text_bytes, meta->nnz, d_entries.p, &lines, &inexact, pairs.data(), cap,
                                     &malformed, 0);
-    cudaFree(d_text);
     if (rc != 0 || malformed || lines < meta->nnz || inexact > cap) {
-        cudaFree(d_entries);
         if (rc == 0 && lines < meta->nnz && !malformed) {  // truncated file: same verdict as the host reader
-            cudaFreeHost(host);
             fprintf(stderr, "Error reading matrix entry %lld (expected 3 items)\n", lines);
             return 4;
         }
-        return host_fallback();
+        return upload_host_entries(filename, meta, d_entries_out);
     }
-    for (int k = 0; k < inexact; k++) {  // literals the exact fast path does not cover: strtod, like fscanf
-        const long long entry = pairs[2 * k], off = pairs[2 * k + 1];
-        const double v = strtod(host + pos + off, nullptr);
-        B200_CUDA(cudaMemcpy(static_cast<char*>(d_entries) + entry * sizeof(Entry) + offsetof(Entry, value), &v,
-                             sizeof(double), cudaMemcpyHostToDevice));
+    // literals the exact fast path does not cover: strtod on the host (like fscanf), then ONE staged
+    // upload + scatter launch instead of one blocking 8-byte copy per literal
+    for (int k = 0; k < inexact; k++) {
+        const double v = strtod(host + pos + pairs[2 * k + 1], nullptr);
+        memcpy(&pairs[2 * k + 1], &v, sizeof v);  // (entry index, byte offset) -> (entry index, value bits)
     }
-    cudaFreeHost(host);
-    *d_entries_out = d_entries;
+    B200_K(b200_patch_entry_values(d_entries.p, pairs.data(), inexact, 0));
+    *d_entries_out = d_entries.release();
     return 0;
 }
 

@@ -276,9 +276,33 @@ extern "C" int write_matrix_market_stencil5(int n, const char* filename) {
 // ------------------------------------------------------------------------------------------------
 // Result: rows in ascending order; inside a row ascending column, equal columns in file order
 // (= counting sort by row that keeps file order, then a stable per-row sort by column).
+// The reference re-uses the global csr_mat whenever (rows, nnz) match (spmv_cusparse_csr.cu:64-69),
+// which silently serves stale values for a second matrix of the same shape.  Here the guard also
+// carries a fingerprint of the source (entries pointer + a strided sample of its content), so the
+// re-use only fires for the matrix the structure was built from.
+namespace {
+uint64_t g_csr_fingerprint = 0, g_ell_fingerprint = 0;
+uint64_t matrix_fingerprint(const MatrixData* mat) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix((uint64_t)mat->rows); mix((uint64_t)mat->cols); mix((uint64_t)mat->nnz); mix((uint64_t)(int64_t)mat->grid_size);
+    if (mat->entries == nullptr) return h | 1;
+    mix((uint64_t)(uintptr_t)mat->entries);
+    const long long nnz = mat->nnz, step = nnz > 4096 ? nnz / 4096 : 1;
+    for (long long k = 0; k < nnz; k += step) {
+        uint64_t bits;
+        memcpy(&bits, &mat->entries[k].value, 8);
+        mix(((uint64_t)(uint32_t)mat->entries[k].row << 32) | (uint32_t)mat->entries[k].col);
+        mix(bits);
+    }
+    return h | 1;
+}
+}  // namespace
+
 int build_csr_struct(struct MatrixData* mat) {
     if (!mat) return EXIT_FAILURE;
-    if (csr_mat.row_ptr != nullptr && csr_mat.nb_rows == mat->rows && csr_mat.nb_nonzeros == mat->nnz) {
+    const uint64_t fp = matrix_fingerprint(mat);
+    if (csr_mat.row_ptr != nullptr && csr_mat.nb_rows == mat->rows && csr_mat.nb_nonzeros == mat->nnz && g_csr_fingerprint == fp) {
         if (!g_quiet) printf("CSR structure already built, reusing (%dx%d, %d nnz)\n", mat->rows, mat->cols, mat->nnz);
         return EXIT_SUCCESS;
     }
@@ -304,6 +328,7 @@ int build_csr_struct(struct MatrixData* mat) {
         rp[mat->rows] = (int)k;
         free(csr_mat.row_ptr); free(csr_mat.col_indices); free(csr_mat.values);
         csr_mat = {mat->rows, mat->cols, mat->nnz, rp, ci, va};
+        g_csr_fingerprint = fp;
         return EXIT_SUCCESS;
     }
     if (!g_quiet) printf("Building CSR structure (%dx%d, %d nnz)...\n", mat->rows, mat->cols, mat->nnz);
@@ -318,7 +343,15 @@ int build_csr_struct(struct MatrixData* mat) {
         free(rp); free(ci); free(va); free(cursor);
         return EXIT_FAILURE;
     }
-    for (int k = 0; k < nnz; k++) rp[E[k].row + 1]++;
+    for (int k = 0; k < nnz; k++) {
+        // a malformed file must not corrupt the heap (or make the device gather read out of bounds)
+        if (E[k].row < 0 || E[k].row >= rows || E[k].col < 0 || E[k].col >= mat->cols) {
+            fprintf(stderr, "[ERROR] entry %d (%d, %d) outside the %d x %d matrix\n", k, E[k].row, E[k].col, rows, mat->cols);
+            free(rp); free(ci); free(va); free(cursor);
+            return EXIT_FAILURE;
+        }
+        rp[E[k].row + 1]++;
+    }
     for (int r = 0; r < rows; r++) { rp[r + 1] += rp[r]; cursor[r] = rp[r]; }
     for (int k = 0; k < nnz; k++) {
         const int d = cursor[E[k].row]++;
@@ -340,6 +373,7 @@ int build_csr_struct(struct MatrixData* mat) {
     // old ones are released when a different matrix replaces them
     free(csr_mat.row_ptr); free(csr_mat.col_indices); free(csr_mat.values);
     csr_mat = {rows, mat->cols, nnz, rp, ci, va};
+    g_csr_fingerprint = fp;
     if (!g_quiet) printf("CSR structure built successfully\n");
     return EXIT_SUCCESS;
 }
@@ -390,12 +424,13 @@ extern "C" int build_ellpack_from_csr_local(CSRMatrix* csr) {
 extern "C" int ensure_ellpack_structure_built(MatrixData* mat) {
     if (build_csr_struct(mat) != EXIT_SUCCESS) return EXIT_FAILURE;
     if (ellpack_matrix.indices != nullptr && ellpack_matrix.nb_rows == mat->rows &&
-        ellpack_matrix.nb_nonzeros == mat->nnz) {
+        ellpack_matrix.nb_nonzeros == mat->nnz && g_ell_fingerprint == g_csr_fingerprint) {
         ellpack_matrix.grid_size = mat->grid_size;
         return EXIT_SUCCESS;
     }
     if (build_ellpack_from_csr_local(&csr_mat) != EXIT_SUCCESS) return EXIT_FAILURE;
     ellpack_matrix.grid_size = mat->grid_size;
+    g_ell_fingerprint = g_csr_fingerprint;
     return EXIT_SUCCESS;
 }
 

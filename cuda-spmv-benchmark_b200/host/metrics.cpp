@@ -135,8 +135,10 @@ std::string now_stamp() {
     return buf;
 }
 
+// reference cg_metrics.cu:68 divides by time_spmv_ms unconditionally ("inf" in the JSON when the timers
+// are off); the engine always fills that field from the device clock, the guard keeps the JSON valid anyway
 double spmv_gflops(const MatrixData* mat, int iterations, double spmv_ms) {
-    return (2.0 * mat->nnz * iterations) / (spmv_ms * 1e6);
+    return spmv_ms > 0.0 ? (2.0 * mat->nnz * iterations) / (spmv_ms * 1e6) : 0.0;
 }
 
 template <class Stats>

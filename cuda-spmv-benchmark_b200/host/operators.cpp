@@ -309,7 +309,7 @@ extern "C" int b200_operator_init_device_coo(SpmvOperator* op, const MatrixData*
     B200_CUDA(cudaMalloc(&b.d_col_idx, ((size_t)meta->nnz + 2) * sizeof(int)));
     B200_CUDA(cudaMalloc(&b.d_values, ((size_t)meta->nnz + 2) * sizeof(double)));
     B200_CUDA(cudaMemset(b.d_values + meta->nnz, 0, 2 * sizeof(double)));
-    int rc = b200_coo_to_csr(d_entries, meta->nnz, meta->rows, b.d_row_ptr, b.d_col_idx, b.d_values, 0);
+    int rc = b200_coo_to_csr(d_entries, meta->nnz, meta->rows, meta->cols, b.d_row_ptr, b.d_col_idx, b.d_values, 0);
     if (rc) { fprintf(stderr, "[b200] %s\n", b200_last_error()); st->reset(); return EXIT_FAILURE; }
     if (st->kind == K_CSR) {
         rc = b200_csr_plan_build(b.d_row_ptr, meta->rows, meta->nnz, &st->plan, 0);

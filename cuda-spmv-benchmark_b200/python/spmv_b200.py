@@ -83,7 +83,23 @@ class Band(C.Structure):  # b200_band, include/b200_kernels.h
                 ("values_len", C.c_longlong), ("row_offset", C.c_longlong), ("n_local", C.c_longlong),
                 ("grid_size", C.c_int), ("layout", C.c_int), ("d_halo_prev", C.c_void_p),
                 ("d_halo_next", C.c_void_p), ("d_flag_prev", C.c_void_p), ("d_flag_next", C.c_void_p),
-                ("epoch", C.c_uint32), ("rows_per_item", C.c_int), ("variant", C.c_int)]
+                ("epoch", C.c_uint32), ("rows_per_item", C.c_int), ("variant", C.c_int), ("d_epoch_ptr", C.c_void_p)]
+
+
+class ReduceCtx(C.Structure):  # b200_reduce_ctx
+    _fields_ = [("d_scalars", C.c_void_p), ("h_status_mapped", C.c_void_p), ("d_partials", C.c_void_p),
+                ("d_partials_b", C.c_void_p), ("d_group_sums", C.c_void_p), ("d_tickets", C.c_void_p),
+                ("capacity", C.c_longlong), ("d_stash", C.c_void_p), ("d_out", C.c_void_p), ("rank", C.c_int),
+                ("world", C.c_int), ("d_peer_xchg", C.c_void_p), ("tol", C.c_double), ("phases", C.c_int)]
+
+
+class HaloPushArgs(C.Structure):  # b200_halo_push_args
+    _fields_ = [("d_dst_prev", C.c_void_p), ("d_dst_next", C.c_void_p), ("d_flag_prev", C.c_void_p),
+                ("d_flag_next", C.c_void_p), ("d_my_xchg", C.c_void_p), ("halo", C.c_int)]
+
+
+class TailTimes(C.Structure):  # b200_cg_tail_times
+    _fields_ = [("ns", C.c_ulonglong * 8), ("count", C.c_uint * 8), ("gap_ns", C.c_ulonglong * 8), ("error", C.c_int)]
 
 
 class CsrPlan(C.Structure):
@@ -100,14 +116,15 @@ C_SYMBOLS = [
     "b200_stencil5_variant_info", "b200_csr_variant_info", "b200_csr_set_default_variant", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
-    "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_update_r_push", "b200_cg_halo_dir",
-    "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_reduce_rr_dir", "b200_csr_dot_partials_capacity",
+    "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_halo_dir",
+    "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_set_pdl", "b200_cg_read_tail_times",
+    "b200_csr_dot_partials_capacity",
     "b200_spmv_csr_dot", "b200_spmv_ellpack_dot", "b200_pcg_diag_inv", "b200_pcg_init", "b200_pcg_update_xr",
-    "b200_pcg_update_p", "b200_pcg_reduce",
-    "b200_dot_partials", "b200_residual_init_generic", "b200_checksum_partials", "b200_halo_push",
-    "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_stencil5_nnz_before",
+    "b200_pcg_update_p",
+    "b200_dot_partials", "b200_residual_init_generic", "b200_checksum", "b200_halo_push",
+    "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_xchg_halo_seq_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
-    "b200_coo_to_csr", "b200_parse_mtx_entries",
+    "b200_coo_to_csr", "b200_patch_entry_values", "b200_parse_mtx_entries",
     # include/b200/api.h, extern "C" part
     "csr_mat", "ellpack_matrix", "build_ellpack_from_csr_local", "ensure_ellpack_structure_built", "get_operator",
     "calculate_spmv_metrics", "get_gpu_properties", "print_benchmark_metrics", "print_metrics_json",
@@ -118,8 +135,9 @@ C_SYMBOLS = [
     # extensions (host/host_common.h)
     "b200_operator_band", "b200_mgpu_init_single_process", "b200_mgpu_init_rank", "b200_mgpu_connect",
     "b200_mgpu_world", "b200_mgpu_rank", "b200_mgpu_finalize", "b200_synthetic_stencil", "b200_set_tuning",
-    "b200_get_tuning", "b200_last_phase_times", "b200_load_matrix_market_device", "b200_operator_init_device_coo",
-    "b200_operator_device_csr", "b200_free_device", "b200_copy_to_host",
+    "b200_get_tuning", "b200_last_phase_times", "b200_last_tail_times", "b200_last_gap_times", "b200_mgpu_halo_probe", "b200_load_matrix_market_device", "b200_operator_init_device_coo",
+    "b200_operator_device_csr", "b200_free_device", "b200_copy_to_host", "b200_host_node_of_device",
+    "b200_host_alloc_near", "b200_host_free",
 ]
 # C++-linkage symbols of the reference API (Itanium mangling)
 CXX_SYMBOLS = {
@@ -131,6 +149,8 @@ CXX_SYMBOLS = {
     "cg_solve_mgpu": "_Z13cg_solve_mgpuP12SpmvOperatorP10MatrixDataPKdPd16CGConfigMultiGPUP15CGStatsMultiGPU",
     "cg_solve_mgpu_partitioned":
         "_Z25cg_solve_mgpu_partitionedP12SpmvOperatorP10MatrixDataPKdPd16CGConfigMultiGPUP15CGStatsMultiGPU",
+    "pcg_solve_mgpu_partitioned":
+        "_Z26pcg_solve_mgpu_partitionedP12SpmvOperatorP10MatrixDataPKdPd16CGConfigMultiGPUP15CGStatsMultiGPU",
     "SPMV_CSR": "SPMV_CSR", "SPMV_STENCIL5_CSR": "SPMV_STENCIL5_CSR",
     "SPMV_STENCIL_HALO_MGPU": "SPMV_STENCIL_HALO_MGPU", "SPMV_ELLPACK": "SPMV_ELLPACK",
     "SPMV_STENCIL5_ELLPACK": "SPMV_STENCIL5_ELLPACK",
@@ -175,33 +195,41 @@ def load():
     L.b200_spmv_csr_dot.argtypes = [C.POINTER(CsrPlan), vp, vp, vp, vp, vp, ll, vp, ll, C.POINTER(i32), vp, vp]
     L.b200_spmv_ellpack_dot.argtypes = [vp, vp, vp, vp, ll, i32, vp, ll, C.POINTER(i32), vp, vp]
     for f in ("b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_xchg_flag_prev_offset",
-              "b200_xchg_flag_next_offset"):
+              "b200_xchg_flag_next_offset", "b200_xchg_halo_seq_offset"):
         getattr(L, f).restype = C.c_size_t
+    ctx, push = C.POINTER(ReduceCtx), C.POINTER(HaloPushArgs)
     L.b200_cg_max_partials.argtypes = [C.POINTER(Band)]
-    L.b200_cg_residual_init.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp, vp, vp]
-    L.b200_cg_spmv_dot.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp]
-    L.b200_cg_update_xr.argtypes = [ll, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
+    L.b200_cg_set_pdl.restype = None
+    L.b200_cg_set_pdl.argtypes = [i32]
+    L.b200_cg_residual_init.argtypes = [C.POINTER(Band), vp, vp, vp, vp, ctx, vp]
+    L.b200_cg_spmv_dot.argtypes = [C.POINTER(Band), vp, vp, ctx, vp]
+    L.b200_cg_update_xr.argtypes = [ll, vp, vp, vp, vp, ctx, vp]
     L.b200_cg_update_p.argtypes = [ll, vp, vp, vp, vp]
-    L.b200_cg_reduce.argtypes = [vp, i32, i32, i32, dbl, vp, vp, vp, i32, i32, C.c_uint32, vp, vp, vp]
-    L.b200_cg_update_p_push.argtypes = [ll, vp, vp, vp, i32, vp, vp, vp, vp, C.c_uint32, vp, vp]
-    L.b200_cg_spmv_fused.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp, vp, vp, vp]
-    L.b200_cg_update_r.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), vp]
-    L.b200_cg_update_r_push.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), i32, vp, vp, vp, vp, C.c_uint32, vp, vp]
-    L.b200_cg_halo_dir.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, C.c_uint32, vp, i32, vp]
+    L.b200_cg_reduce.argtypes = [ctx, i32, i32, i32, i32, vp]
+    L.b200_cg_update_p_push.argtypes = [ll, vp, vp, vp, push, vp]
+    L.b200_cg_spmv_fused.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp, ctx, vp]
+    L.b200_cg_update_r.argtypes = [ll, vp, vp, push, ctx, vp]
+    L.b200_cg_halo_dir.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]
     L.b200_cg_finish_x.argtypes = [ll, vp, vp, vp, vp, vp]
     L.b200_cg_set_schedule.restype = None
     L.b200_cg_set_schedule.argtypes = [i32]
-    L.b200_dot_partials.argtypes = [ll, vp, vp, vp, vp, C.POINTER(i32), vp]
-    L.b200_residual_init_generic.argtypes = [ll, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
-    L.b200_checksum_partials.argtypes = [ll, vp, vp, vp, C.POINTER(i32), vp]
-    L.b200_halo_push.argtypes = [vp, ll, i32, vp, vp, vp, vp, C.c_uint32, vp, vp, vp]
+    L.b200_cg_read_tail_times.argtypes = [vp, C.POINTER(TailTimes), vp]
+    L.b200_dot_partials.argtypes = [ll, vp, vp, ctx, vp]
+    L.b200_residual_init_generic.argtypes = [ll, vp, vp, vp, vp, ctx, vp]
+    L.b200_checksum.argtypes = [ll, vp, ctx, vp]
+    L.b200_halo_push.argtypes = [vp, ll, push, vp, vp]
+    L.b200_pcg_diag_inv.argtypes = [vp, vp, vp, ll, ll, i32, vp, vp, vp]
+    L.b200_pcg_init.argtypes = [ll, vp, vp, vp, ctx, vp]
+    L.b200_pcg_update_xr.argtypes = [ll, vp, vp, vp, vp, vp, ctx, vp]
+    L.b200_pcg_update_p.argtypes = [ll, vp, vp, vp, vp, push, vp]
     L.b200_stencil5_nnz_before.restype = ll
     L.b200_stencil5_nnz_before.argtypes = [ll, ll]
     L.b200_gen_stencil5_csr.argtypes = [i32, ll, ll, dbl, dbl, vp, vp, vp, vp]
     L.b200_gen_stencil5_ellpack.argtypes = [i32, ll, ll, dbl, dbl, vp, vp, vp]
     L.b200_gen_stencil5_entries.argtypes = [i32, ll, ll, dbl, dbl, vp, vp]
     L.b200_fill.argtypes = [vp, ll, dbl, vp]
-    L.b200_coo_to_csr.argtypes = [vp, ll, i32, vp, vp, vp, vp]
+    L.b200_coo_to_csr.argtypes = [vp, ll, i32, i32, vp, vp, vp, vp]
+    L.b200_patch_entry_values.argtypes = [vp, vp, i32, vp]
     L.b200_parse_mtx_entries.argtypes = [vp, ll, ll, vp, C.POINTER(ll), C.POINTER(i32), vp, i32, C.POINTER(i32), vp]
     # host API
     L.get_operator.restype = C.POINTER(SpmvOperator)
@@ -232,12 +260,19 @@ def load():
     L.b200_synthetic_stencil.argtypes = [i32]
     L.b200_set_tuning.argtypes = [i32, i32]
     L.b200_last_phase_times.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
+    L.b200_last_tail_times.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
+    L.b200_last_gap_times.argtypes = [C.POINTER(dbl)]
+    L.b200_mgpu_halo_probe.argtypes = [i32, C.POINTER(dbl), C.POINTER(ll)]
     L.b200_load_matrix_market_device.argtypes = [C.c_char_p, C.POINTER(MatrixData), C.POINTER(vp)]
     L.b200_operator_init_device_coo.argtypes = [C.POINTER(SpmvOperator), C.POINTER(MatrixData), vp]
     L.b200_operator_device_csr.argtypes = [C.POINTER(SpmvOperator), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ll)]
     L.b200_free_device.argtypes = [vp]
     L.b200_free_device.restype = None
     L.b200_copy_to_host.argtypes = [vp, vp, C.c_size_t]
+    L.b200_host_node_of_device.argtypes = [i32]
+    L.b200_host_alloc_near.argtypes = [i32, C.c_size_t, C.POINTER(vp), C.POINTER(i32)]
+    L.b200_host_free.argtypes = [vp]
+    L.b200_host_free.restype = None
     # C++-linkage entry points
     L.build_csr_struct = getattr(L, CXX_SYMBOLS["build_csr_struct"])
     L.build_csr_struct.argtypes = [C.POINTER(MatrixData)]
@@ -247,7 +282,7 @@ def load():
         f = getattr(L, CXX_SYMBOLS[nm])
         f.argtypes = [C.POINTER(SpmvOperator), C.POINTER(MatrixData), vp, vp, CGConfig, C.POINTER(CGStats)]
         setattr(L, nm, f)
-    for nm in ("cg_solve_mgpu", "cg_solve_mgpu_partitioned"):
+    for nm in ("cg_solve_mgpu", "cg_solve_mgpu_partitioned", "pcg_solve_mgpu_partitioned"):
         f = getattr(L, CXX_SYMBOLS[nm])
         f.argtypes = [C.POINTER(SpmvOperator), C.POINTER(MatrixData), vp, vp, CGConfig, C.POINTER(CGStatsMultiGPU)]
         setattr(L, nm, f)

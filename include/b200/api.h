@@ -104,5 +104,9 @@ int cg_solve_mgpu(SpmvOperator* spmv_op, MatrixData* mat, const double* b, doubl
                   CGConfigMultiGPU config, CGStatsMultiGPU* stats);
 int cg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
                               CGConfigMultiGPU config, CGStatsMultiGPU* stats);
+/* extension: Jacobi-preconditioned CG over the same row-band partition (arguments of
+ * cg_solve_mgpu_partitioned; the edges of the preconditioned direction travel like p does there) */
+int pcg_solve_mgpu_partitioned(SpmvOperator* spmv_op, MatrixData* mat, const double* b, double* x,
+                               CGConfigMultiGPU config, CGStatsMultiGPU* stats);
 
 #endif /* B200_API_H */

@@ -48,7 +48,9 @@ unsigned long long b200_launch_count(void);
  * (src/spmv/spmv_stencil_partitioned_halo_kernel.cu:17-21): grid_size doubles each, NULL when
  * there is no neighbour.  d_flag_prev/next (optional) are 32-bit arrival epochs in THIS GPU's
  * memory, release-stored by the neighbours' b200_halo_push; rows that read a halo wait until
- * flag >= epoch, all other rows run immediately (transfer overlaps the interior).
+ * flag >= epoch (or *d_epoch_ptr: this rank's own halo sequence counter, which equals the
+ * neighbours' because every rank pushes in the same phases), all other rows run immediately
+ * (transfer overlaps the interior).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     const int* d_row_ptr;
@@ -66,6 +68,7 @@ typedef struct {
     uint32_t epoch;
     int rows_per_item; /* tuning: grid rows marched per warp item, 0 = default */
     int variant;       /* tuning: kernel instantiation, 0 = default (see b200_stencil5_variant_info) */
+    const uint32_t* d_epoch_ptr; /* if set, the number to wait for is read from here (device) instead of `epoch` */
 } b200_band;
 
 /* y = A x on the band.  Stands in for the launches at spmv_stencil_csr_direct.cu:230-240,267-271
@@ -129,117 +132,164 @@ int b200_spmv_ellpack_dot(const int* d_indices, const double* d_values, const do
                           int* n_partials_out, const void* d_scalars, b200_stream stream);
 
 /* ---- fused CG steps ---------------------------------------------------------------------
- * d_scalars: b200_cg_scalars_bytes() bytes of device memory (zero it before a solve).
- * d_partials: scratch for per-CTA partial sums, at least b200_cg_max_partials(band) doubles.
- * Replaces the 11-launch iteration of cg_solve_device (src/solvers/cg_solver.cu:538-638).      */
+ * Replaces the 11-launch iteration of cg_solve_device (src/solvers/cg_solver.cu:538-638).
+ *
+ * Reduction context (one per rank).  Every kernel below that produces a dot product writes one
+ * partial sum per CTA.  The BLAS-1 kernels (a few hundred long-lived CTAs) end with a *tail*: the
+ * last CTA to finish (ticket counters) adds the partials in a fixed two-level order, exchanges the
+ * total with the other ranks over peer memory and applies the scalar recurrence.  The STENCIL5
+ * kernels (O(1e5) short CTAs, where a ticket per CTA would cost 3 %) are followed by a small reduce
+ * kernel that does the same in the same order, launched programmatically behind them (no launch gap).
+ * Either way: no host round trip, identical bits.  Replaces
+ * dot_kernel / final_sum_kernel / scalar_divide_kernel / check_convergence_kernel
+ * (cg_solver.cu:110-132,384-431) and, multi-GPU, cublasDdot + MPI_Allreduce
+ * (cg_solver_mgpu_partitioned.cu:145-154,531,583,645).
+ *   d_scalars      b200_cg_scalars_bytes() bytes, zeroed before a solve
+ *   h_status_mapped  optional pinned+mapped b200_cg_status_bytes() block the host may poll
+ *   d_partials(_b) capacity doubles each; d_group_sums 2*ceil(capacity/256) doubles;
+ *   d_tickets      1+ceil(capacity/256) 32-bit counters, zeroed ONCE (self-resetting)
+ *   d_stash        2 doubles; d_out 2 doubles (which = 3)
+ *   d_peer_xchg    world device pointers to every rank's exchange area (b200_xchg_bytes() bytes,
+ *                  zeroed once), as mapped in this process; NULL when world == 1
+ *   phases         3: whole reduction inside the producing kernel.  1: local total + stores to the
+ *                  peers only -- b200_cg_reduce(phases = 2) must follow once every rank's producer
+ *                  has been enqueued (several ranks on one stream).  0: partials only,
+ *                  b200_cg_reduce(phases = 3) does the rest.
+ * Exchange sequence numbers (scalar exchanges, halo pushes) are counted ON THE DEVICE inside the
+ * exchange areas: ranks stay in lockstep however many no-op iterations each host enqueues. */
+typedef struct {
+    void* d_scalars;
+    void* h_status_mapped;
+    double* d_partials;
+    double* d_partials_b;
+    double* d_group_sums;
+    uint32_t* d_tickets;
+    long long capacity;
+    double* d_stash;
+    double* d_out;
+    int rank, world;
+    void* const* d_peer_xchg;
+    double tol;
+    int phases;
+} b200_reduce_ctx;
+
+/* which: 0 = r0.r0 (sets rr_old, b_norm), 1 = p.Ap (alpha), 2 = r.r (convergence test, beta,
+ * iteration count), 3 = plain sum(s) into d_out, 4 = PCG rho_0, 5 = PCG r.r + r.z */
+enum { B200_RED_RR0 = 0, B200_RED_PAP = 1, B200_RED_RR = 2, B200_RED_SUM = 3, B200_RED_RZ0 = 4, B200_RED_PCG = 5 };
+
 size_t b200_cg_scalars_bytes(void);
 size_t b200_cg_status_bytes(void);
 size_t b200_xchg_bytes(void);
+/* partial sums the STENCIL5 kernels write for this band (= their grid size, halo CTAs included) */
 int b200_cg_max_partials(const b200_band* band);
+/* programmatic dependent launch in the iteration loop (the next kernel is scheduled while the tail of
+ * the previous one runs; every such kernel starts with griddepcontrol.wait).  mode bit 0: the small
+ * kernels (reduce, halo direction, finish_x), bit 1: the STENCIL5 kernels; default 3.  The persistent
+ * BLAS-1 kernels always launch the normal way (a dependent launch stacks their CTAs unevenly over the
+ * SMs).  env B200_PDL=<0..3> */
+void b200_cg_set_pdl(int mode);
 
-/* setup: r = b - A x ; p = r ; partials <- r.r          (cg_solver.cu:498-517) */
+/* Halo addressing of a band inside a multi-GPU solve: where neighbours write, what to wait for. */
+typedef struct {
+    double* d_dst_prev;      /* rank-1's landing buffer for MY first `halo` elements (peer memory) */
+    double* d_dst_next;      /* rank+1's landing buffer for my last `halo` elements */
+    uint32_t* d_flag_prev;   /* rank-1's arrival word for them */
+    uint32_t* d_flag_next;
+    void* d_my_xchg;         /* this rank's exchange area */
+    int halo;                /* elements per edge = grid_size */
+} b200_halo_push_args;
+
+/* setup: r = b - A x ; p = r ; r.r -> rr_old, b_norm           (cg_solver.cu:498-528) */
 int b200_cg_residual_init(const b200_band* band, const double* d_x, const double* d_b, double* d_r,
-                          double* d_p, double* d_partials, void* d_scalars, b200_stream stream);
-/* K1: Ap = A p ; partials <- p.Ap                         (cg_solver.cu:541-551) */
-int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double* d_Ap, double* d_partials,
-                     const void* d_scalars, b200_stream stream);
-/* K2: x += alpha p ; r -= alpha Ap ; partials <- r.r      (cg_solver.cu:564-585) */
-int b200_cg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
-                      double* d_x, double* d_r, double* d_partials, int* n_partials_out,
-                      b200_stream stream);
-/* K3: p = r + beta p                                      (cg_solver.cu:628) */
+                          double* d_p, const b200_reduce_ctx* ctx, b200_stream stream);
+/* K1: Ap = A p ; p.Ap -> alpha                                  (cg_solver.cu:541-560) */
+int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double* d_Ap, const b200_reduce_ctx* ctx,
+                     b200_stream stream);
+/* K2: x += alpha p ; r -= alpha Ap ; r.r -> convergence, beta   (cg_solver.cu:564-637) */
+int b200_cg_update_xr(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r,
+                      const b200_reduce_ctx* ctx, b200_stream stream);
+/* K3: p = r + beta p                                            (cg_solver.cu:628) */
 int b200_cg_update_p(long long n, const void* d_scalars, const double* d_r, double* d_p,
                      b200_stream stream);
 
-/* R: fixed-order sum of partials (+ rank exchange) and the scalar recurrences.
- * which: 0 = r0.r0 (sets rr_old, b_norm), 1 = p.Ap (alpha), 2 = r.r (convergence test, beta,
- * iteration count), 3 = plain sum into d_out.
- * phases: 1 = local sum + push to peers, 2 = wait for peers + recurrences, 3 = both in one launch.
- * Multi-rank: d_peer_xchg[world] are every rank's exchange areas as mapped in this process,
- * epoch must be the same on all ranks for the same reduction and differ between reductions.
- * Replaces dot_kernel/final_sum_kernel/scalar_divide_kernel/check_convergence_kernel and, on
- * the multi-GPU path, cublasDdot + MPI_Allreduce (cg_solver_mgpu_partitioned.cu:145-154,531). */
-int b200_cg_reduce(const double* d_partials, int n_partials, int which, int phases, double tol,
-                   void* d_scalars, void* h_status_mapped, double* d_out, int rank, int world,
-                   uint32_t epoch, void* const* d_peer_xchg, double* d_stash, b200_stream stream);
+/* R: the same fixed-order sum + exchange + recurrence as a launch of its own (operators behind
+ * run_device; the wait half when several ranks share one stream; exchanges without data). */
+int b200_cg_reduce(const b200_reduce_ctx* ctx, int which, int n_partials, int two_sums, int phases,
+                   b200_stream stream);
 
 /* generic helpers for operators without a fused entry point */
-int b200_dot_partials(long long n, const void* d_scalars, const double* d_x, const double* d_y,
-                      double* d_partials, int* n_partials_out, b200_stream stream);
+int b200_dot_partials(long long n, const double* d_x, const double* d_y, const b200_reduce_ctx* ctx,
+                      b200_stream stream);
 int b200_residual_init_generic(long long n, const double* d_b, const double* d_Ap, double* d_r,
-                               double* d_p, double* d_partials, int* n_partials_out, b200_stream stream);
-/* sum(x) and sum(x^2) partials, n_partials_out each            (cg_solver.cu:658-665) */
-int b200_checksum_partials(long long n, const double* d_x, double* d_psum, double* d_psq,
-                           int* n_partials_out, b200_stream stream);
+                               double* d_p, const b200_reduce_ctx* ctx, b200_stream stream);
+/* sum(x) -> d_out[0], sum(x^2) -> d_out[1], over all ranks        (cg_solver.cu:658-665) */
+int b200_checksum(long long n, const double* d_x, const b200_reduce_ctx* ctx, b200_stream stream);
 
 /* Halo push over NVLink peer memory.  Replaces exchange_halo_mpi
- * (cg_solver_mgpu_partitioned.cu:173-231).  dst pointers / flags live in the NEIGHBOURS' memory
- * (peer-mapped); d_my_xchg is this rank's exchange area. */
-int b200_halo_push(const double* d_v_local, long long n_local, int halo, double* d_dst_prev,
-                   double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next, uint32_t epoch,
-                   void* d_my_xchg, const void* d_scalars, b200_stream stream);
-/* K3 with the halo push fused in: p = r + beta p, the first / last `halo` elements are also stored
- * into the neighbours' landing buffers and the arrival epoch is published by the last CTA. */
-int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p, int halo,
-                          double* d_dst_prev, double* d_dst_next, uint32_t* d_flag_prev,
-                          uint32_t* d_flag_next, uint32_t epoch, void* d_my_xchg, b200_stream stream);
+ * (cg_solver_mgpu_partitioned.cu:173-231): the first / last `halo` elements of d_v_local are
+ * stored into the neighbours' landing buffers, the last CTA bumps this rank's halo sequence number
+ * and release-stores it into the neighbours' arrival words. */
+int b200_halo_push(const double* d_v_local, long long n_local, const b200_halo_push_args* h,
+                   const void* d_scalars, b200_stream stream);
+/* K3 with the halo push fused in */
+int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r, double* d_p,
+                          const b200_halo_push_args* h, b200_stream stream);
 
-/* ---- "deferred x" CG schedule: 4 launches and 112 B/row per iteration ----------------------
+/* ---- "deferred x" CG schedule: 112 B/row per iteration -----------------------------------
  * Same recurrences as cg_solve_device (src/solvers/cg_solver.cu:538-638), regrouped:
  *   b200_cg_spmv_fused : p_new = r + beta p_old (update_p_kernel :91-96), x += alpha_prev p_old
- *                        (axpy_kernel_device :59-66, one iteration late), Ap = A p_new and the p.Ap
- *                        partials, in ONE pass of the STENCIL5 kernel.  band halos hold the NEW p.
- *   b200_cg_update_r   : r -= alpha Ap (axpy_sub_kernel_device :70-78) and the r.r partials, summed
- *                        in the order of b200_cg_update_xr.  The _push form also stores the first /
- *                        last `halo` elements of r into the neighbours' landing buffers.
- *   b200_cg_halo_dir   : halo copies of p follow the same recurrence from the pushed r edges.
+ *                        (axpy_kernel_device :59-66, one iteration late), Ap = A p_new, p.Ap -> alpha,
+ *                        in ONE pass of the STENCIL5 kernel.  band halos hold the NEW p.
+ *   b200_cg_update_r   : r -= alpha Ap (axpy_sub_kernel_device :70-78), r.r -> convergence, beta,
+ *                        summed in the order of b200_cg_update_xr.  push != NULL: the first / last
+ *                        `halo` elements of r also go into the neighbours' landing buffers.
+ *   b200_cg_halo_dir   : halo copies of p follow the same recurrence from the pushed r edges,
+ *                        p_halo = fma(beta, p_halo_old, r_halo) (beta_zero: first direction, p0 = r0).
  *   b200_cg_finish_x   : the x update still pending after the last iteration.
- * Every iterate is bit-identical to the 5-launch schedule.                                      */
+ * Every iterate is bit-identical to the classic K1 / K2 / K3 schedule.                          */
 int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
-                       double* d_x, double* d_Ap, double* d_partials, const void* d_scalars,
-                       b200_stream stream);
-int b200_cg_update_r(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
-                     double* d_partials, int* n_partials_out, b200_stream stream);
-int b200_cg_update_r_push(long long n, const void* d_scalars, const double* d_Ap, double* d_r,
-                          double* d_partials, int* n_partials_out, int halo, double* d_dst_prev,
-                          double* d_dst_next, uint32_t* d_flag_prev, uint32_t* d_flag_next,
-                          uint32_t epoch, void* d_my_xchg, b200_stream stream);
+                       double* d_x, double* d_Ap, const b200_reduce_ctx* ctx, b200_stream stream);
+int b200_cg_update_r(long long n, const double* d_Ap, double* d_r, const b200_halo_push_args* push,
+                     const b200_reduce_ctx* ctx, b200_stream stream);
 int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const double* d_pold_prev,
                      const double* d_pold_next, double* d_pnew_prev, double* d_pnew_next, int halo,
-                     const uint32_t* d_flag_prev, const uint32_t* d_flag_next, uint32_t epoch,
+                     const uint32_t* d_flag_prev, const uint32_t* d_flag_next, const void* d_my_xchg,
                      void* d_scalars, int beta_zero, b200_stream stream);
-/* b200_cg_reduce(which = 2) and b200_cg_halo_dir in one launch: once beta is known the reduce CTA
- * advances the halo copies of the direction (multi-GPU, deferred-x schedule) */
-int b200_cg_reduce_rr_dir(const double* d_partials, int n_partials, int phases, double tol, void* d_scalars,
-                          void* h_status_mapped, int rank, int world, uint32_t epoch,
-                          void* const* d_peer_xchg, double* d_stash, const double* d_r_prev,
-                          const double* d_r_next, const double* d_pold_prev, const double* d_pold_next,
-                          double* d_pnew_prev, double* d_pnew_next, int halo, const uint32_t* d_flag_prev,
-                          const uint32_t* d_flag_next, uint32_t halo_epoch, b200_stream stream);
 int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
                      double* d_x, b200_stream stream);
-/* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 5-launch schedule;
+/* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 3-launch schedule;
  * the environment variable B200_CG_SCHEDULE=classic selects 0 at start-up */
 void b200_cg_set_schedule(int deferred_x);
-/* ---- Jacobi-preconditioned CG (single GPU) --------------------------------------------------
+/* device-measured time spent in the reduction tails of a solve, per `which` */
+typedef struct {
+    unsigned long long ns[8];      /* time inside the tails */
+    unsigned int count[8];
+    unsigned long long gap_ns[8];  /* time between the end of the previous tail and the begin of this one: the
+                                      kernel(s) that produced the partial sums (no events needed) */
+    int error;
+} b200_cg_tail_times;
+int b200_cg_read_tail_times(const void* d_scalars, b200_cg_tail_times* h_out, b200_stream stream);
+
+/* ---- Jacobi-preconditioned CG ----------------------------------------------------------------
  * Not in the reference (its cg_solver.h:6-7 / README name preconditioning as the next step): the
  * textbook recurrence over the conventions of cg_solve_device (cg_solver.cu:498-638).  z = D^-1 r is
- * never stored.  rho = r.z lives in the scalar block where plain CG keeps r.r, so b200_cg_spmv_dot /
- * b200_cg_reduce(which = 1) serve unchanged; b200_cg_reduce(which = 4) stores rho_0.               */
+ * never stored.  rho = r.z lives in the scalar block where plain CG keeps r.r, so b200_cg_spmv_dot
+ * serves unchanged.  Multi-GPU: K3p pushes the edges of the new p like b200_cg_update_p_push. */
 int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
                       long long row_offset, int ell_width, double* d_dinv, int* d_err, b200_stream stream);
-int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, double* d_partials,
-                  int* n_partials_out, b200_stream stream);
-int b200_pcg_update_xr(long long n, const void* d_scalars, const double* d_p, const double* d_Ap,
-                       const double* d_dinv, double* d_x, double* d_r, double* d_partials_rr,
-                       double* d_partials_rz, int* n_partials_out, b200_stream stream);
+/* p0 = z0 = D^-1 r0 ; r0.z0 -> rho_0 */
+int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, const b200_reduce_ctx* ctx,
+                  b200_stream stream);
+/* K2p: x += alpha p ; r -= alpha Ap ; r.r -> convergence ; r.z -> beta, rho */
+int b200_pcg_update_xr(long long n, const double* d_p, const double* d_Ap, const double* d_dinv, double* d_x,
+                       double* d_r, const b200_reduce_ctx* ctx, b200_stream stream);
+/* K3p: p = D^-1 r + beta p (push != NULL: + halo push) */
 int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
-                      b200_stream stream);
-int b200_pcg_reduce(const double* d_partials_rr, const double* d_partials_rz, int n_partials, double tol,
-                    void* d_scalars, void* h_status_mapped, b200_stream stream);
-/* offsets of the halo flags inside an exchange area */
+                      const b200_halo_push_args* push, b200_stream stream);
+/* offsets of the halo arrival words / the halo sequence counter inside an exchange area */
 size_t b200_xchg_flag_prev_offset(void);
 size_t b200_xchg_flag_next_offset(void);
+size_t b200_xchg_halo_seq_offset(void);
 
 /* ---- device-side matrix construction (bit-identical to generator -> reader -> CSR build) ---- */
 long long b200_stencil5_nnz_before(long long row, long long grid_size);
@@ -256,9 +306,13 @@ int b200_fill(double* d_p, long long n, double value, b200_stream stream);
 /* ---- device-side ingest (arbitrary matrices) -----------------------------------------------
  * COO -> CSR on the device, bit-identical to build_csr_struct (src/spmv/spmv_cusparse_csr.cu:85-157):
  * rows ascending, columns ascending inside a row, equal columns in input order.  d_entries is an
- * array of {int row; int col; double value;} (0-based).  d_row_ptr: rows+1 ints. */
-int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int* d_row_ptr, int* d_col_idx,
+ * array of {int row; int col; double value;} (0-based).  d_row_ptr: rows+1 ints.  Entries with a row
+ * outside [0, rows) or a column outside [0, cols) (cols <= 0: only negative columns) are rejected. */
+int b200_coo_to_csr(const void* d_entries, long long nnz, int rows, int cols, int* d_row_ptr, int* d_col_idx,
                     double* d_values, b200_stream stream);
+/* entries[pair[2k]].value = bits pair[2k+1], k < n: one staged upload + one launch (values the host
+ * re-read with strtod after b200_parse_mtx_entries) */
+int b200_patch_entry_values(void* d_entries, const long long* h_pairs, int n, b200_stream stream);
 /* Parses the ENTRY lines of a Matrix Market file ("i j value", 1-based) held in device memory into
  * d_entries (0-based), like the fscanf loop of src/io/io.cu:153-166.  n_lines_out = non-blank lines
  * found; literals outside the exact fast path are listed as (entry index, byte offset of the value

@@ -290,6 +290,38 @@ def test_pcg_jacobi_matches_oracle_and_beats_cg(B, orc, torch_cuda, opname, n):
     assert np.linalg.norm(xp - xc) / np.linalg.norm(xc) < 1e-5
 
 
+@pytest.mark.parametrize("n,P", [(40, 2), (130, 3), (257, 4)])
+def test_pcg_mgpu_virtual_ranks_matches_oracle(B, orc, torch_cuda, n, P):
+    """pcg_solve_mgpu_partitioned over P row bands (virtual ranks on one GPU): bands cut from the caller's
+    entries, 1 / diag(A) per band, the edges of the preconditioned direction pushed by K3p -- same
+    iteration count as the oracle, solution within 1e-10, and equal to the one-GPU PCG.  Two different
+    matrices of the SAME shape back to back: the second solve must not see the first one's values."""
+    L = B.load()
+    N = n * n
+    devs = (C.c_int * P)(*([0] * P))
+    rng = np.random.default_rng(n + P)
+    b = rng.standard_normal(N)
+    for seed in (n, n + 1):
+        ent = variable_diagonal_stencil(orc, n, seed)
+        hm = B.HostMatrix.from_entries(N, N, ent, grid_size=n)
+        orp, oci, ova = orc.build_csr(N, N, ent)
+        xo, ro = orc.pcg_device(orp, oci, ova, n, 1, b, np.zeros(N))
+        x1, s1, op = solve_device(B, b"stencil5-csr", hm, b, np.zeros(N), entry="pcg_solve_device")
+        op.contents.free()
+        assert L.b200_mgpu_init_single_process(P, devs, n) == 0
+        try:
+            x = np.zeros(N)
+            st = B.CGStatsMultiGPU()
+            rc = L.pcg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(), C.byref(st))
+            assert rc == 0
+            assert st.converged == 1 and st.iterations == ro["iterations"] == s1["iterations"]
+            assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+            assert np.linalg.norm(x - x1) / np.linalg.norm(x1) < 1e-12
+            assert abs(st.residual_norm - ro["residual_norm"]) <= 1e-9 * ro["b_norm"]
+        finally:
+            L.b200_mgpu_finalize()
+
+
 def test_pcg_constant_diagonal_equals_cg_iterations(B, orc, torch_cuda):
     """on the 5 / -1 stencil D = 5 I: PCG is CG in exact arithmetic -- same iteration count"""
     n = 300

@@ -22,7 +22,7 @@ def device_csr(B, torch, ent, rows):
     rp = torch.full((rows + 1,), -7, dtype=torch.int32, device="cuda")
     ci = torch.full((max(nnz, 1),), -7, dtype=torch.int32, device="cuda")
     va = torch.zeros(max(nnz, 1), dtype=torch.float64, device="cuda")
-    B.check(L.b200_coo_to_csr(dptr(d_ent), nnz, rows, dptr(rp), dptr(ci), dptr(va), None), "coo_to_csr")
+    B.check(L.b200_coo_to_csr(dptr(d_ent), nnz, rows, 0, dptr(rp), dptr(ci), dptr(va), None), "coo_to_csr")
     return rp.cpu().numpy(), ci.cpu().numpy()[:nnz], va.cpu().numpy()[:nnz]
 
 
@@ -67,8 +67,13 @@ def test_coo_to_csr_rejects_bad_rows(B, orc, torch_cuda):
     rp = torch_cuda.zeros(4, dtype=torch_cuda.int32, device="cuda")
     ci = torch_cuda.zeros(3, dtype=torch_cuda.int32, device="cuda")
     va = torch_cuda.zeros(3, dtype=torch_cuda.float64, device="cuda")
-    assert L.b200_coo_to_csr(dptr(d_ent), 3, 3, dptr(rp), dptr(ci), dptr(va), None) == 1
+    assert L.b200_coo_to_csr(dptr(d_ent), 3, 3, 3, dptr(rp), dptr(ci), dptr(va), None) == 1
     assert b"row index" in L.b200_last_error()
+    ent["row"] = [0, 2, 1]
+    ent["col"] = [0, 3, 1]  # column 3 of a 3-column matrix
+    d_ent = torch_cuda.from_numpy(np.frombuffer(ent.tobytes(), dtype=np.uint8).copy()).cuda()
+    assert L.b200_coo_to_csr(dptr(d_ent), 3, 3, 3, dptr(rp), dptr(ci), dptr(va), None) == 1
+    assert b"column index" in L.b200_last_error()
 
 
 def load_device(B, torch, path):
@@ -164,3 +169,33 @@ def test_mtx_parse_fallbacks_and_errors(B, orc, torch_cuda, tmp_path):
     open(p, "w").write("%%MatrixMarket matrix coordinate real general\n2 2 3\n1 1 1.0\n")
     assert load_device(B, torch_cuda, p)[0] != 0
     assert load_device(B, torch_cuda, str(tmp_path / "nope.mtx"))[0] != 0
+
+
+def test_cli_device_ingest_flag(B, orc, torch_cuda, tmp_path):
+    """`spmv_bench` / `cg_solver --device-ingest`: the .mtx is parsed and turned into CSR on the GPU (no host
+    Entry[] / CSR); answers equal the host-reader path -- bundled 81 x 81 matrix (centre -4): Sum(y) = -52164,
+    CG 40 iterations, Sum(x) = -826.0838884."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "cuda-spmv-benchmark_b200", "bin")
+    mtx = str(tmp_path / "example81x81.mtx")
+    orc.write_mtx_stencil5(81, mtx, "-4.0", "-1.0")
+    outs = {}
+    for flag in ([], ["--device-ingest"]):
+        r = subprocess.run([os.path.join(bindir, "spmv_bench"), mtx, "--mode=stencil5-csr,cusparse-csr"] + flag,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        sums = [float(v) for v in re.findall(r"Sum\(y\):\s+([-+0-9.eE]+)", r.stdout)]
+        assert sums == [-52164.0, -52164.0]
+        r = subprocess.run([os.path.join(bindir, "cg_solver"), mtx, "--mode=stencil5-csr"] + flag,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert "Converged: YES in 40 iterations" in r.stdout
+        outs[bool(flag)] = re.search(r"Sum\(x\):\s+([-+0-9.eE]+)", r.stdout).group(1)
+        if flag:
+            assert "parsed on the device" in r.stdout
+    assert outs[False] == outs[True] and abs(float(outs[True]) + 826.0838884) < 1e-6
+    r = subprocess.run([os.path.join(bindir, "spmv_bench"), mtx, "--mode=ellpack", "--device-ingest"], capture_output=True, text=True)
+    assert r.returncode != 0 and "supports the cusparse-csr and stencil5-csr" in r.stderr

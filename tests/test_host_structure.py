@@ -230,3 +230,31 @@ def test_synthetic_matrix_beyond_32_bit_rows(B):
     for r in range(8):
         lo, hi = r * (N // 8), (r + 1) * (N // 8)
         assert 0 < L.b200_stencil5_nnz_before(hi, n) - L.b200_stencil5_nnz_before(lo, n) < 2**31
+
+
+def test_csr_cache_is_keyed_on_the_matrix_not_only_its_shape(B, orc):
+    """the reference re-uses its global csr_mat whenever (rows, nnz) match (spmv_cusparse_csr.cu:64-69);
+    here a second matrix of the same shape must get its own values, while the SAME matrix is not rebuilt.
+    Entries outside the matrix are rejected instead of corrupting the heap."""
+    import numpy as np
+    L = B.load()
+    n = 12
+    N = n * n
+    e1 = orc.stencil5_entries(n, 5.0, -1.0)
+    e2 = e1.copy()
+    e2["value"] = np.where(e2["row"] == e2["col"], 7.5, -2.0)
+    h1 = B.HostMatrix.from_entries(N, N, e1, grid_size=n)
+    h2 = B.HostMatrix.from_entries(N, N, e2, grid_size=n)
+    assert L.build_csr_struct(h1.ptr()) == 0
+    _, _, va1 = B.host_csr_arrays()
+    ptr1 = C.cast(B.csr_mat().values, C.c_void_p).value
+    assert L.build_csr_struct(h1.ptr()) == 0  # same matrix: re-used, not rebuilt
+    assert C.cast(B.csr_mat().values, C.c_void_p).value == ptr1
+    assert L.build_csr_struct(h2.ptr()) == 0  # same shape, other values: rebuilt
+    rp2, ci2, va2 = B.host_csr_arrays()
+    orp, oci, ova = orc.build_csr(N, N, e2)
+    assert np.array_equal(va2, ova) and np.array_equal(ci2, oci) and not np.array_equal(va1, va2)
+    bad = e1.copy()
+    bad["col"][5] = N + 3
+    hb = B.HostMatrix.from_entries(N, N, bad, grid_size=n)
+    assert L.build_csr_struct(hb.ptr()) != 0

@@ -87,14 +87,29 @@ def main():
     rec("torch_copy_4GiB", ms, best, 2.0 * big.numel() * 8)
     del big, big2
 
+    def reduce_ctx(capacity, phases=3):
+        """b200_reduce_ctx over fresh device buffers (fused reduction tail inside the producing kernel)"""
+        groups = (capacity + 255) // 256
+        t = {"sc": torch.zeros(64, dtype=torch.float64, device="cuda"),
+             "pa": torch.empty(capacity, dtype=torch.float64, device="cuda"),
+             "pb": torch.empty(capacity, dtype=torch.float64, device="cuda"),
+             "gs": torch.empty(2 * groups, dtype=torch.float64, device="cuda"),
+             "tk": torch.zeros(groups + 1, dtype=torch.int32, device="cuda"),
+             "st": torch.zeros(4, dtype=torch.float64, device="cuda")}
+        t["sc"][0] = 1.0   # rr_old
+        t["sc"][3] = 0.5   # alpha
+        t["sc"][4] = 0.25  # beta
+        t["sc"][5] = 1.0   # b_norm
+        c = B.ReduceCtx(t["sc"].data_ptr(), None, t["pa"].data_ptr(), t["pb"].data_ptr(), t["gs"].data_ptr(),
+                        t["tk"].data_ptr(), capacity, t["st"].data_ptr(), t["st"].data_ptr() + 16, 0, 1, None, 0.0, phases)
+        c._keep = t
+        return c
+
     if "stencil" in what:
         st_bytes = 8.0 * nnz + 16.0 * N
-        partials = torch.empty(1 << 22, dtype=torch.float64, device="cuda")
+        ctx = reduce_ctx(1 << 20)
         if "fused" in what:
             fr, fp, fx = (torch.ones(N, dtype=torch.float64, device="cuda") for _ in range(3))
-            fsc = torch.zeros(64, dtype=torch.float64, device="cuda")
-            fsc[3] = 0.5   # alpha
-            fsc[4] = 0.25  # beta
         for v in [int(t) for t in a.variants.split(",")]:
             info = L.b200_stencil5_variant_info(v)
             if info is None:
@@ -105,33 +120,33 @@ def main():
                 ms, best = timeit(lambda: B.check(L.b200_stencil5_spmv(C.byref(band), dptr(x), dptr(y), s), "st"))
                 ok = float(y.sum().item()) == N + 4 * n
                 rec("stencil5_plain", ms, best, st_bytes, variant=v, rows_per_item=R, ok=ok)
-                ms, best = timeit(lambda: B.check(L.b200_cg_spmv_dot(C.byref(band), dptr(x), dptr(y), dptr(partials),
-                                                                     None, s), "dot"))
-                rec("stencil5_dot", ms, best, st_bytes, variant=v, rows_per_item=R)
+                ms, best = timeit(lambda: B.check(L.b200_cg_spmv_dot(C.byref(band), dptr(x), dptr(y), C.byref(ctx), s), "dot"))
+                rec("stencil5_dot+tail", ms, best, st_bytes, variant=v, rows_per_item=R)
                 if "fused" in what:
-                    ms, best = timeit(lambda: B.check(L.b200_cg_spmv_fused(C.byref(band), dptr(x), dptr(fr), dptr(fp), dptr(fx),
-                                                                           dptr(y), dptr(partials), dptr(fsc), s), "fused"))
-                    rec("stencil5_fused(K1F)", ms, best, 8.0 * nnz + 48.0 * N, variant=v, rows_per_item=R)
-        del partials
+                    ms, best = timeit(lambda: B.check(L.b200_cg_spmv_fused(C.byref(band), dptr(x), dptr(fr), dptr(fp),
+                                                                           dptr(fx), dptr(y), C.byref(ctx), s), "fused"))
+                    rec("stencil5_fused(K1F)+tail", ms, best, 8.0 * nnz + 48.0 * N, variant=v, rows_per_item=R)
+        del ctx
 
     if "cg" in what:
-        sc = torch.zeros(64, dtype=torch.float64, device="cuda")
-        sc[3] = 0.5  # alpha
-        sc[4] = 0.25  # beta
+        ctx = reduce_ctx(1 << 16)
+        sc = ctx._keep["sc"]
         p, Ap, xx, r = (torch.ones(N, dtype=torch.float64, device="cuda") for _ in range(4))
-        partials = torch.empty(4096, dtype=torch.float64, device="cuda")
-        npart = C.c_int()
-        ms, best = timeit(lambda: B.check(L.b200_cg_update_xr(N, dptr(sc), dptr(p), dptr(Ap), dptr(xx), dptr(r),
-                                                              dptr(partials), C.byref(npart), s), "k2"))
-        rec("cg_update_xr(K2)", ms, best, 48.0 * N)
+
+        def keep_going():  # the timed kernels are no-ops once `converged` is set
+            sc[7] = 0.0  # converged / iterations
+        keep_going()
+        ms, best = timeit(lambda: B.check(L.b200_cg_update_xr(N, dptr(p), dptr(Ap), dptr(xx), dptr(r), C.byref(ctx), s), "k2"))
+        rec("cg_update_xr(K2)+tail", ms, best, 48.0 * N)
+        keep_going()
         ms, best = timeit(lambda: B.check(L.b200_cg_update_p(N, dptr(sc), dptr(r), dptr(p), s), "k3"))
         rec("cg_update_p(K3)", ms, best, 24.0 * N)
-        ms, best = timeit(lambda: B.check(L.b200_cg_update_r(N, dptr(sc), dptr(Ap), dptr(r), dptr(partials), C.byref(npart), s), "k2r"))
-        rec("cg_update_r(K2r)", ms, best, 24.0 * N)
-        ms, best = timeit(lambda: B.check(L.b200_cg_reduce(dptr(partials), 1184, 3, 3, 1e-6, None, None, dptr(sc),
-                                                           0, 1, 1, None, None, s), "red"))
-        rec("cg_reduce(1184 partials)", ms, best, 1184 * 8.0)
-        del p, Ap, xx, r
+        keep_going()
+        ms, best = timeit(lambda: B.check(L.b200_cg_update_r(N, dptr(Ap), dptr(r), None, C.byref(ctx), s), "k2r"))
+        rec("cg_update_r(K2r)+tail", ms, best, 24.0 * N)
+        ms, best = timeit(lambda: B.check(L.b200_cg_reduce(C.byref(ctx), 3, 1184, 0, 3, s), "red"))
+        rec("cg_reduce(1184 partials, stand-alone)", ms, best, 1184 * 8.0)
+        del p, Ap, xx, r, ctx
 
     cvars = [int(t) for t in a.csr_variants.split(",")]
     if "csr" in what:
