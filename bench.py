@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--single-process", action="store_true",
                     help="N > 1 without torchrun: ONE process drives all N GPUs (one enqueue thread per GPU), the "
                          "north-star topology / the reference CLI's `cg_solver_mgpu_stencil`")
+    ap.add_argument("--host-buffers", default="near", choices=["near", "torch"],
+                    help="pinned host vectors: 'near' = library allocator, pages on the GPU's NUMA node; 'torch' = pin_memory()")
     ap.add_argument("--timers-every", type=int, default=4,
                     help="record the per-phase CUDA events (roofline.avg_launch_ms) on every K-th timed step only: an event "
                          "between two kernels keeps the second one from being scheduled under the tail of the first "
@@ -328,8 +330,24 @@ def run_b200(args):
     import mgpu_bootstrap
     nl, off = (N, 0) if single else mgpu_bootstrap.partition(N, world, rank)
     # pinned host buffers of the local slice; the solver only touches [off, off+nl) of b and x
-    b_host = torch.ones(nl, dtype=torch.float64).pin_memory()
-    x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
+    host_node = None
+    near_ptrs = []
+
+    def host_vector(fill):
+        """pinned host vector of this rank's rows: the library's NUMA-aware allocator (host/host_alloc.cpp) or torch"""
+        nonlocal host_node
+        if args.host_buffers == "near" and not single:
+            p, node = C.c_void_p(), C.c_int(-1)
+            if L.b200_host_alloc_near(local_rank, 8 * nl, C.byref(p), C.byref(node)) == 0:
+                host_node = node.value
+                near_ptrs.append(p)
+                t = torch.frombuffer((C.c_double * nl).from_address(p.value), dtype=torch.float64)
+                t.fill_(fill)
+                return t
+        return torch.full((nl,), fill, dtype=torch.float64).pin_memory()
+
+    b_host = host_vector(1.0)
+    x_host = host_vector(0.0)
     b_ptr = b_host.data_ptr() - off * 8
     x_ptr = x_host.data_ptr() - off * 8
     cfg_timed = B.cg_config(MAX_ITERS, TOL, 0, 1)  # detailed timers: event records only, no extra syncs
@@ -484,7 +502,9 @@ def run_b200(args):
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 16 * nl, "d2h_bytes_per_step": 8 * nl,
                 "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
                 "pcie_gbs_per_rank": round(24.0 * nl / world_div / max((e2e_ms - ms) * 1e-3, 1e-9) / 1e9, 2),
-                "host_buffers": "pinned", "block_wall_ms_per_step": block_ms / args.steps},
+                "host_buffers": ("pinned, first-touched on NUMA node %s (GPU's own node: %s)"
+                                 % (host_node, L.b200_host_node_of_device(local_rank))) if near_ptrs else "pinned (torch pin_memory)",
+                "block_wall_ms_per_step": block_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -536,6 +556,9 @@ def run_b200(args):
         line["operators_10k"] = operator_table(L, B, torch, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del b_host, x_host  # 6.4 GB of pinned host memory the CPU arm can use
+        for p_ in near_ptrs:
+            L.b200_host_free(p_)
+        near_ptrs.clear()
         cpu = CpuCG(n, args.cpu_grid)
         v = cpu.solve()
         line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "grid": cpu.n,

@@ -17,6 +17,8 @@
 //     groups with long rows go warp-per-row (butterfly sum, tolerance 1e-12).
 // ELLPACK (row-major, padding index -1) is the same code with row_ptr[r] = r * width.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -431,8 +433,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) csr_ring_kernel(const CsrArg
         }
         return sum;
     };
+    // sub-warp rows: S lanes per row, 32 / S rows of the group at a time -- for groups whose longest row has
+    // at most 2 * S... 4 * S entries, where a whole warp per row would leave most lanes idle (9..64-entry rows
+    // that do not fit the lane-per-row ring).  Lane j of a row's S lanes takes the entries j, j + S, ... in
+    // k order, a butterfly over the S lanes closes the row.
+    auto process_sub = [&](const CsrGroup& G, int rows_here, auto s_tag) {
+        constexpr int S = decltype(s_tag)::value, R = 32 / S;
+        double sum = 0.0;
+        const int sub = lane / S, j0 = lane % S;
+        for (int q0 = 0; q0 < rows_here; q0 += R) {
+            const int qlast = min(q0 + R, rows_here) - 1;
+            const int first = __shfl_sync(B200_FULL, G.s, q0);
+            const int last_end = __shfl_sync(B200_FULL, G.s + G.len, qlast);
+            release(first);
+            ensure(last_end);
+            const int r = min(q0 + sub, qlast);  // lanes past the last row redo it (their result is not used)
+            const int rs = __shfl_sync(B200_FULL, G.s, r);
+            const int re = rs + __shfl_sync(B200_FULL, G.len, r);
+            double part = 0.0;
+            for (int kk = rs + j0; kk < re; kk += S) {
+                const int c = scol[kk & M];
+                if (!ELL || c >= 0) part = fma(sval[kk & M], __ldg(xp + c), part);
+            }
+#pragma unroll
+            for (int o = S / 2; o > 0; o >>= 1) part += __shfl_xor_sync(B200_FULL, part, o);
+            const double mine = __shfl_sync(B200_FULL, part, ((lane - q0) & (R - 1)) * S);
+            if (lane >= q0 && lane <= qlast) sum = mine;
+        }
+        return sum;
+    };
     // warp-per-row: the rows of the group one after the other, streamed through the ring
     auto process_vec = [&](const CsrGroup& G, int rows_here) {
+        if (G.maxlen <= 32) return process_sub(G, rows_here, std::integral_constant<int, 8>());
+        if (G.maxlen <= 64) return process_sub(G, rows_here, std::integral_constant<int, 16>());
         double sum = 0.0;
         for (int q = 0; q < rows_here; q++) {
             const int qs = __shfl_sync(B200_FULL, G.s, q);
