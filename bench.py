@@ -449,10 +449,10 @@ def run_b200(args):
 
     ms = sum(dev_ms) / len(dev_ms)
     e2e_ms = sum(wall_ms) / len(wall_ms)
-    world_div = world if single else 1  # rows per RANK behind nl
     peak, peak_src = measured_peak()
-    rows_local = nl
-    nnz_local = L.b200_stencil5_nnz_before(off + nl, n) - L.b200_stencil5_nnz_before(off, n)
+    # per-RANK band (the roofline / byte models below are per GPU); a single process holds all the bands
+    rows_local, off_rank = mgpu_bootstrap.partition(N, world, 0) if single else (nl, off)
+    nnz_local = L.b200_stencil5_nnz_before(off_rank + rows_local, n) - L.b200_stencil5_nnz_before(off_rank, n)
     # Dominant kernel: the STENCIL5 SpMV.  Deferred-x schedule (default): the first launch of a solve is
     # the plain SpMV + p.Ap (values + p + Ap = 8 nnz + 16 N bytes), every later one is the fused
     # direction-update SpMV (values + r + p_old + x in, p_new + x + Ap out = 8 nnz + 48 N bytes);
@@ -477,8 +477,8 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get(traffic_key)
-            if traffic is not None:  # captured on the full matrix: scale to this rank's band
-                traffic = traffic * nnz_local / float(5 * N - 4 * n)
+            if world > 1:  # the ncu capture is of the one-GPU launch: not a measurement of a band
+                traffic = None
         except Exception:
             traffic = None
     if deferred_x:
@@ -497,11 +497,11 @@ def run_b200(args):
         "config": {"workload": "cg_%dx%d_stencil5_b1_x0_tol1e-6" % (n, n), "grid": n, "rows": N,
                    "nnz": 5 * N - 4 * n, "tol": TOL, "iterations": iters, "operator": "stencil5-csr",
                    "partition": "row bands x%d" % world,
-                   "rows_per_gpu": nl,
+                   "rows_per_gpu": rows_local,
                    "cache": "vectors (3.2 GB each) and matrix (16 GB values) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": 16 * nl, "d2h_bytes_per_step": 8 * nl,
                 "api": "cg_solve_device" if world == 1 else "cg_solve_mgpu_partitioned",
-                "pcie_gbs_per_rank": round(24.0 * nl / world_div / max((e2e_ms - ms) * 1e-3, 1e-9) / 1e9, 2),
+                "pcie_gbs_per_rank": round(24.0 * rows_local / max((e2e_ms - ms) * 1e-3, 1e-9) / 1e9, 2),
                 "host_buffers": ("pinned, first-touched on NUMA node %s (GPU's own node: %s)"
                                  % (host_node, L.b200_host_node_of_device(local_rank))) if near_ptrs else "pinned (torch pin_memory)",
                 "block_wall_ms_per_step": block_ms / args.steps},

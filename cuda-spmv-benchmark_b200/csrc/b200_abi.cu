@@ -13,8 +13,12 @@
 #include "generate.cuh"
 #include "ingest.cuh"
 #include "stencil5.cuh"
+#include "stencil5_direct.cuh"
 #include "stencil_layout.h"
 
+#ifndef B200_PLAIN_VARIANT_DEFAULT
+#define B200_PLAIN_VARIANT_DEFAULT 0
+#endif
 #ifndef B200_PDL_DEFAULT
 #define B200_PDL_DEFAULT 3
 #endif
@@ -86,25 +90,28 @@ struct Variant {
     int cols, warps, stages;
     const char* info;
 };
-// keep in sync with the dispatch switch below
+// Tuning variants that are compiled in.  Round 1 swept fourteen shapes (profiles/, gpurun_out/sweep_*): only
+// the default is used in production; the others that survive are the ones a measurement still compares
+// against (3-stage ring, 8 warps, 2 warps).  Pruned ids fall back to the default.  Keep in sync with the
+// dispatch switch below.
 const Variant kVariants[] = {
     {4, 4, 2, "v0 (default): 128-col strips (4 cols/lane), 4 warps/CTA, 2-stage ring"},
-    {1, 4, 4, "v1: 32-col strips (1 col/lane), 4 warps/CTA, 4-stage ring"},
-    {2, 8, 4, "v2: 64-col strips, 8 warps/CTA, 4-stage ring"},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
     {4, 4, 3, "v3: 128-col strips (4 cols/lane), 4 warps/CTA, 3-stage ring"},
-    {2, 4, 3, "v4: 64-col strips, 4 warps/CTA, 3-stage ring"},
-    {2, 2, 4, "v5: 64-col strips, 2 warps/CTA, 4-stage ring"},
-    {4, 2, 3, "v6: 128-col strips, 2 warps/CTA, 3-stage ring"},
-    {2, 4, 4, "v7: 64-col strips, 4 warps/CTA, 4-stage ring"},
-    {2, 1, 4, "v8: 64-col strips, 1 warp/CTA, 4-stage ring"},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
     {2, 2, 3, "v9: 64-col strips (2 cols/lane), 2 warps/CTA, 3-stage ring (round-1 default until the K1F sweep)"},
-    {4, 1, 3, "v10: 128-col strips, 1 warp/CTA, 3-stage ring"},
-    {2, 4, 2, "v11: 64-col strips, 4 warps/CTA, 2-stage ring"},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
     {4, 8, 2, "v12: 128-col strips, 8 warps/CTA, 2-stage ring"},
     {4, 2, 2, "v13: 128-col strips, 2 warps/CTA, 2-stage ring"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-const int kDefaultRowsPerItem = 8;
+const int kDefaultRowsPerItem = 4;  // round-2 sweep (profiles/sweep_r02.md): 4 rows beat 8 by 1-1.5 % on the plain and dot kernels, equal on K1F
 constexpr int kMaxDevices = 64;
 int current_device() {
     int dev = 0;
@@ -128,7 +135,7 @@ int build_geometry(const b200_band* b, const double* x, Geometry* g) {
     if (!b->d_values || !b->d_col_idx) return fail(B200_EINVAL, "stencil5: NULL matrix arrays");
     if (b->layout == 0 && !b->d_row_ptr) return fail(B200_EINVAL, "stencil5: CSR layout needs row_ptr");
     if (((uintptr_t)b->d_values & 15) != 0) return fail(B200_EINVAL, "stencil5: values must be 16-byte aligned");
-    const int v = (b->variant >= 0 && b->variant < kNumVariants) ? b->variant : 0;
+    const int v = (b->variant >= 0 && b->variant < kNumVariants && kVariants[b->variant].info) ? b->variant : 0;
     const Variant& V = kVariants[v];
     Stencil5Args& a = g->a;
     memset(&a, 0, sizeof a);
@@ -207,17 +214,8 @@ int launch_one(const Geometry& g, cudaStream_t s) {
 template <int MODE, bool CG>
 int launch_variant(int v, const Geometry& g, cudaStream_t s) {
     switch (v) {
-        case 1: return launch_one<MODE, 1, 4, 4, CG>(g, s);
-        case 2: return launch_one<MODE, 2, 8, 4, CG>(g, s);
         case 3: return launch_one<MODE, 4, 4, 3, CG>(g, s);
-        case 4: return launch_one<MODE, 2, 4, 3, CG>(g, s);
-        case 5: return launch_one<MODE, 2, 2, 4, CG>(g, s);
-        case 6: return launch_one<MODE, 4, 2, 3, CG>(g, s);
-        case 7: return launch_one<MODE, 2, 4, 4, CG>(g, s);
-        case 8: return launch_one<MODE, 2, 1, 4, CG>(g, s);
         case 9: return launch_one<MODE, 2, 2, 3, CG>(g, s);
-        case 10: return launch_one<MODE, 4, 1, 3, CG>(g, s);
-        case 11: return launch_one<MODE, 2, 4, 2, CG>(g, s);
         case 12: return launch_one<MODE, 4, 8, 2, CG>(g, s);
         case 13: return launch_one<MODE, 4, 2, 2, CG>(g, s);
         default: return launch_one<MODE, 4, 4, 2, CG>(g, s);
@@ -227,7 +225,7 @@ int launch_variant(int v, const Geometry& g, cudaStream_t s) {
 template <int MODE>
 int launch_stencil(const b200_band* b, Geometry& g, cudaStream_t s) {
     if (g.grid == 0) return B200_OK;
-    const int v = (b->variant >= 0 && b->variant < kNumVariants) ? b->variant : 0;
+    const int v = (b->variant >= 0 && b->variant < kNumVariants && kVariants[b->variant].info) ? b->variant : 0;
     // peer-written halos must be read through L2 (ld.global.cg); single-GPU uses the read-only path
     const bool cg = (b->d_halo_prev != nullptr || b->d_halo_next != nullptr);
     return cg ? launch_variant<MODE, true>(v, g, s) : launch_variant<MODE, false>(v, g, s);
@@ -236,6 +234,9 @@ int launch_stencil(const b200_band* b, Geometry& g, cudaStream_t s) {
 }  // namespace
 
 extern "C" const char* b200_stencil5_variant_info(int v) {
+    if (v == 20) return "v20: sequential sweep, 1 row per thread (plain SpMV only)";
+    if (v == 21) return "v21: sequential sweep, 2 rows per thread (plain SpMV only)";
+    if (v == 22) return "v22: sequential sweep, 4 rows per thread (plain SpMV only)";
     return (v >= 0 && v < kNumVariants) ? kVariants[v].info : nullptr;
 }
 
@@ -246,12 +247,39 @@ extern "C" int b200_stencil5_num_partials(const b200_band* band) {
     return g.grid;
 }
 
+namespace {
+// plain product, sequential-sweep form (csrc/stencil5_direct.cuh): variants 20 / 21 / 22 = 1 / 2 / 4 rows per thread
+template <int ROWS>
+int launch_direct(const b200_band* b, const Geometry& g, cudaStream_t s) {
+    const long long threads = (g.a.n_local + ROWS - 1) / ROWS;
+    const long long blocks = (threads + 255) / 256;
+    if (blocks == 0) return B200_OK;
+    if (blocks > 2147483647LL) return fail(B200_EINVAL, "stencil5: too many blocks");
+    const bool cg = (b->d_halo_prev != nullptr || b->d_halo_next != nullptr);
+    if (cg) stencil5_direct_kernel<ROWS, true><<<(unsigned)blocks, 256, 0, s>>>(g.a);
+    else stencil5_direct_kernel<ROWS, false><<<(unsigned)blocks, 256, 0, s>>>(g.a);
+    return check_launch("stencil5_direct_kernel");
+}
+std::atomic<int> g_plain_variant{B200_PLAIN_VARIANT_DEFAULT};
+}  // namespace
+
+// variant used by b200_stencil5_spmv when the band asks for the default (0): 0 = bulk-copy ring, 20..22 = sweep
+extern "C" void b200_stencil5_set_plain_variant(int v) { g_plain_variant.store(v, std::memory_order_relaxed); }
+
 extern "C" int b200_stencil5_spmv(const b200_band* band, const double* d_x, double* d_y, b200_stream stream) {
     Geometry g;
     int rc = build_geometry(band, d_x, &g);
     if (rc) return rc;
     if (!d_y) return fail(B200_EINVAL, "stencil5: NULL y");
     g.a.y = d_y;
+    int v = band->variant;
+    if (v == 0) v = g_plain_variant.load(std::memory_order_relaxed);
+    // the sweep form has no flag waits: bands whose halos are still in flight stay on the ring kernel
+    if (v >= 20 && v <= 22 && !band->d_flag_prev && !band->d_flag_next) {
+        if (v == 20) return launch_direct<1>(band, g, (cudaStream_t)stream);
+        if (v == 21) return launch_direct<2>(band, g, (cudaStream_t)stream);
+        return launch_direct<4>(band, g, (cudaStream_t)stream);
+    }
     return launch_stencil<ST_PLAIN>(band, g, (cudaStream_t)stream);
 }
 
@@ -290,16 +318,16 @@ struct CsrVariant {
     int warps, stages, win;
     const char* info;
 };
-// keep in sync with the dispatch switch in launch_csr
+// c0 and c6 are what b200_csr_plan_build picks; the other ring shapes of the round-1 sweep
+// (profiles/csr_ring_r01.md) are pruned.  Keep in sync with the dispatch switch in launch_csr_variant.
 const CsrVariant kCsrVariants[] = {
     {8, 4, 128, "c0 (default): 8 warps/CTA, ring of 4 x 128-entry windows, 4 CTAs/SM"},
-    {8, 4, 128, "c1: 8 warps/CTA, ring of 4 x 128-entry windows, 3 CTAs/SM"},
-    {8, 4, 256, "c2: 8 warps/CTA, ring of 4 x 256-entry windows, 2 CTAs/SM"},
-    {4, 4, 256, "c3: 4 warps/CTA, ring of 4 x 256-entry windows, 4 CTAs/SM"},
-    {8, 8, 64, "c4: 8 warps/CTA, ring of 8 x 64-entry windows, 4 CTAs/SM"},
-    {4, 4, 128, "c5: 4 warps/CTA, ring of 4 x 128-entry windows, 8 CTAs/SM"},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
+    {0, 0, 0, nullptr},
     {8, 8, 128, "c6: 8 warps/CTA, ring of 8 x 128-entry windows, 2 CTAs/SM"},
-    {16, 4, 128, "c7: 16 warps/CTA, ring of 4 x 128-entry windows, 2 CTAs/SM"},
 };
 const int kNumCsrVariants = (int)(sizeof(kCsrVariants) / sizeof(kCsrVariants[0]));
 
@@ -361,13 +389,7 @@ int launch_csr_ring(const CsrArgs& a, int gpw, cudaStream_t s) {
 template <bool ELL>
 int launch_csr_variant(int v, int gpw, const CsrArgs& a, cudaStream_t s) {
     switch (v) {
-        case 1: return launch_csr_ring<8, 4, 128, ELL, 3>(a, gpw, s);
-        case 2: return launch_csr_ring<8, 4, 256, ELL, 2>(a, gpw, s);
-        case 3: return launch_csr_ring<4, 4, 256, ELL, 4>(a, gpw, s);
-        case 4: return launch_csr_ring<8, 8, 64, ELL, 4>(a, gpw, s);
-        case 5: return launch_csr_ring<4, 4, 128, ELL, 8>(a, gpw, s);
         case 6: return launch_csr_ring<8, 8, 128, ELL, 2>(a, gpw, s);
-        case 7: return launch_csr_ring<16, 4, 128, ELL, 2>(a, gpw, s);
         default: return launch_csr_ring<8, 4, 128, ELL, 4>(a, gpw, s);
     }
 }
@@ -393,7 +415,7 @@ int launch_csr(const CsrArgs& a, int variant, cudaStream_t s) {
         if (a.dot_partials) return fail(B200_EINVAL, "csr: the fused dot needs 16-byte aligned col_idx / values");
         return launch_csr_legacy(a, s);
     }
-    if (variant >= kNumCsrVariants) variant = 0;
+    if (variant >= kNumCsrVariants || !kCsrVariants[variant].info) variant = 0;
     if (a.dot_partials) {  // fused x.y partials: compiled for the default variant only
         if (a.row_ptr) return launch_csr_ring_mode<8, 4, 128, 0, 4, true>(a, gpw, s);
         return csr_ring_ell_is_lpr<4, 128>(a.ell_width) ? launch_csr_ring_mode<8, 4, 128, 1, 4, true>(a, gpw, s)

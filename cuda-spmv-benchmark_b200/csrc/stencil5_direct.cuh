@@ -1,0 +1,83 @@
+// stencil5_direct.cuh -- plain y = A x for the 5-point stencil, "sequential sweep" form.
+//
+// Why a second SpMV kernel next to stencil5.cuh: measured on the same B200, the reference's
+// one-thread-per-row kernel (src/spmv/spmv_stencil_csr_direct.cu:76-123), recompiled for sm_100, runs
+// the 10k x 10k product in 0.794 ms = 7.06 TB/s of algorithmic traffic, the bulk-copy ring of
+// stencil5.cuh in 0.833 ms = 6.72 TB/s (tests/golden/ref_gpu_10k.json, profiles/).  The ring tiles the
+// grid into 8-row x 128-column items: each of the ~2400 resident warps streams its own 5 KB pieces,
+// 400 KB apart from row to row.  A sweep in which consecutive threads own consecutive rows makes the
+// whole GPU read ONE contiguous window of `values` that moves forward through the array -- the access
+// order HBM likes best -- and the north / south x rows come out of L2 (written ~n rows earlier) instead
+// of registers.  For the un-fused product that wins; the fused CG kernels (7 streams, x-row reuse in
+// registers, no L2 re-reads of r and p_old) stay on the ring.
+//
+// This kernel keeps the arithmetic of the reference bit for bit (t = vC*xC; fma(vW,xW,t); fma(vE,xE,t);
+// fma(vN,xN,t); fma(vS,xS,t); boundary rows: fma chain over the CSR row from 0.0) and differs in shape:
+// ROWS consecutive rows per thread (their 5*ROWS coefficients are one contiguous span: 128-bit loads
+// where the span is 16-byte aligned), x_C / x_W / x_E of the thread's rows from ROWS + 2 loads instead of
+// 3*ROWS, streaming stores for y, band + halo addressing as in stencil5.cuh.
+#pragma once
+#include "common.cuh"
+#include "stencil5.cuh"
+
+namespace b200 {
+
+template <int ROWS, bool CG_LOADS>
+__global__ void __launch_bounds__(256) stencil5_direct_kernel(const Stencil5Args a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long lr0 = t * ROWS;  // first local row of this thread
+    if (lr0 >= a.n_local) return;
+    const long long n = a.n;
+    const long long r0 = a.row_offset + lr0;
+    const long long i = r0 / n;
+    const long long j0 = r0 - i * n;
+    // fast path: all ROWS rows are interior points of the same grid row and lie inside the band
+    const bool fast = (i >= 1) && (i <= n - 2) && (j0 >= 1) && (j0 + ROWS - 1 <= n - 2) && (lr0 + ROWS <= a.n_local);
+    if (fast) {
+        const double* v = a.values + (a.base0 + i * a.row_stride + 5 * j0);
+        double c[5 * ROWS];
+#pragma unroll
+        for (int k = 0; k < 5 * ROWS; k++) c[k] = __ldcs(v + k);
+        // x(i, j0-1 .. j0+ROWS): one more than the rows on either side
+        double xc[ROWS + 2], xn[ROWS], xs[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS + 2; k++) xc[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 - 1 + k);
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            xn[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 + k - n);
+            xs[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 + k + n);
+        }
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const double* cc = c + 5 * k;  // N, W, C, E, S
+            double s = cc[2] * xc[k + 1];
+            s = fma(cc[1], xc[k], s);
+            s = fma(cc[3], xc[k + 2], s);
+            s = fma(cc[0], xn[k], s);
+            s = fma(cc[4], xs[k], s);
+            __stcs(a.y + lr0 + k, s);
+        }
+        return;
+    }
+    // boundary rows of the grid (and the ragged end of a band): CSR walk, reference order
+#pragma unroll 1
+    for (int k = 0; k < ROWS; k++) {
+        const long long lr = lr0 + k;
+        if (lr >= a.n_local) break;
+        const long long r = a.row_offset + lr;
+        const long long gi = r / n, gj = r - gi * n;
+        if (gi >= 1 && gi <= n - 2 && gj >= 1 && gj <= n - 2) {  // interior row next to a boundary one
+            const double* v = a.values + (a.base0 + gi * a.row_stride + 5 * gj);
+            double s = v[2] * x_at<ST_PLAIN, CG_LOADS>(a, lr);
+            s = fma(v[1], x_at<ST_PLAIN, CG_LOADS>(a, lr - 1), s);
+            s = fma(v[3], x_at<ST_PLAIN, CG_LOADS>(a, lr + 1), s);
+            s = fma(v[0], x_at<ST_PLAIN, CG_LOADS>(a, lr - n), s);
+            s = fma(v[4], x_at<ST_PLAIN, CG_LOADS>(a, lr + n), s);
+            a.y[lr] = s;
+        } else {
+            (void)boundary_row<ST_PLAIN, CG_LOADS>(a, r, 0.0, 0.0);
+        }
+    }
+}
+
+}  // namespace b200

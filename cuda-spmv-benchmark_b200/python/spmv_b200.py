@@ -113,7 +113,7 @@ C_SYMBOLS = [
     # include/b200_kernels.h
     "b200_version", "b200_last_error", "b200_launch_count", "b200_stencil5_spmv", "b200_spmv_stencil5_csr",
     "b200_spmv_stencil5_halo", "b200_spmv_stencil5_ellpack", "b200_stencil5_num_partials",
-    "b200_stencil5_variant_info", "b200_csr_variant_info", "b200_csr_set_default_variant", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
+    "b200_stencil5_variant_info", "b200_stencil5_set_plain_variant", "b200_csr_variant_info", "b200_csr_set_default_variant", "b200_csr_plan_build", "b200_spmv_csr", "b200_spmv_ellpack",
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_halo_dir",
@@ -183,6 +183,8 @@ def load():
     L.b200_stencil5_num_partials.argtypes = [C.POINTER(Band)]
     L.b200_stencil5_variant_info.restype = C.c_char_p
     L.b200_stencil5_variant_info.argtypes = [i32]
+    L.b200_stencil5_set_plain_variant.restype = None
+    L.b200_stencil5_set_plain_variant.argtypes = [i32]
     L.b200_csr_variant_info.restype = C.c_char_p
     L.b200_csr_variant_info.argtypes = [i32]
     L.b200_csr_set_default_variant.restype = None

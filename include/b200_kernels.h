@@ -88,6 +88,9 @@ int b200_spmv_stencil5_ellpack(const double* d_values, const int* d_col_indices,
                                double* d_y, int num_rows, int width, double alpha, double beta,
                                int grid_size, b200_stream stream);
 
+/* kernel behind b200_stencil5_spmv when a band asks for the default: 0 = bulk-copy ring (csrc/stencil5.cuh),
+ * 20 / 21 / 22 = sequential sweep with 1 / 2 / 4 rows per thread (csrc/stencil5_direct.cuh) */
+void b200_stencil5_set_plain_variant(int v);
 /* number of per-CTA partial sums the fused kernels below write for this band */
 int b200_stencil5_num_partials(const b200_band* band);
 /* human-readable description of tuning variant v (NULL past the last one) */

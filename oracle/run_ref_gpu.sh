@@ -4,6 +4,12 @@
 # printed checksums / iteration counts into gpurun_out/ref_gpu.json -- the golden vectors that pin
 # the oracle's numeric functions (tests/test_oracle_golden.py).  Test infrastructure only.
 #   usage (on the GPU box, repo root):  bash oracle/run_ref_gpu.sh
+#   REF_GPU_SIZES="10000:5" REF_GPU_OUT=ref_gpu_10k bash oracle/run_ref_gpu.sh
+#       -> the reference's own kernels on THIS B200 at a BASELINE size (a 12 GB .mtx written by the reference's
+#          generator, read back by its fscanf loader): the "A100 kernels recompiled for sm_100" bar of SURVEY 2a.
+#          Note the reference cg_solver CLI keeps x between its warm-ups and the measured solves
+#          (src/main/cg_solver.cu:155-173): its iteration count / median belong to warm restarts, so the
+#          per-iteration time (median_ms / iterations) is the comparable figure.
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/ref_gpu
@@ -13,14 +19,18 @@ import json, os, re, subprocess, sys, time
 sys.path.insert(0, "oracle")
 import orc
 out = "gpurun_out/ref_gpu"
+name = os.environ.get("REF_GPU_OUT", "ref_gpu")
+sizes = [(int(t.split(":")[0]), float(t.split(":")[1])) for t in
+         os.environ.get("REF_GPU_SIZES", "81:-4,64:5,512:5,1000:5,2000:5").split(",")]
 cases = []
-for n, center in ((81, -4.0), (64, 5.0), (512, 5.0), (1000, 5.0), (2000, 5.0)):
+for n, center in sizes:
     mtx = os.path.join(out, "s%d.mtx" % n)
     if center == -4.0:
         orc.write_mtx_stencil5(n, mtx, "-4.0", "-1.0")   # byte-identical to matrix/example81x81.mtx
     else:
         subprocess.run(["oracle/_ref/generate_matrix", str(n), mtx], check=True, stdout=subprocess.DEVNULL)
-    case = {"n": n, "center": center, "spmv": {}, "cg": {}}
+    case = {"n": n, "center": center, "spmv": {}, "cg": {}, "mtx_bytes": os.path.getsize(mtx)}
+    t_case = time.time()
     r = subprocess.run(["oracle/_ref/spmv_bench", mtx, "--mode=stencil5-csr,cusparse-csr",
                         "--json=%s/spmv_%d.json" % (out, n)], capture_output=True, text=True)
     open(os.path.join(out, "spmv_%d.log" % n), "w").write(r.stdout + r.stderr)
@@ -42,11 +52,14 @@ for n, center in ((81, -4.0), (64, 5.0), (512, 5.0), (1000, 5.0), (2000, 5.0)):
                               "residual_norm": j["convergence"]["residual_norm"],
                               "solution_sum": j["validation"]["solution_sum"],
                               "solution_norm": j["validation"]["solution_norm"], "median_ms": j["timing"]["median_ms"]}
+    for op, c in case["cg"].items():
+        c["ms_per_iteration"] = c["median_ms"] / max(c["iterations"], 1)
+    case["wall_s"] = round(time.time() - t_case, 1)
     cases.append(case)
     os.remove(mtx)
 gpu = subprocess.run(["nvidia-smi", "--query-gpu=name,driver_version", "--format=csv,noheader"],
                      capture_output=True, text=True).stdout.strip()
 json.dump({"generator": "oracle/run_ref_gpu.sh: reference spmv_bench / cg_solver (oracle/_ref, -arch=sm_100) on " + gpu,
-           "cases": cases}, open("gpurun_out/ref_gpu.json", "w"), indent=1)
+           "cases": cases}, open("gpurun_out/%s.json" % name, "w"), indent=1)
 print(json.dumps(cases)[:2000])
 PY

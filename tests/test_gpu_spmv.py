@@ -73,7 +73,7 @@ def test_device_generation_band_slices(B, orc, torch_cuda, n, P):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 33, 34, 64, 65, 66, 67, 81, 130, 257, 600])
-@pytest.mark.parametrize("variant", [0, 1, 3, 9, 12, 13])
+@pytest.mark.parametrize("variant", [0, 3, 9, 12, 13, 20, 21, 22])
 def test_stencil5_csr_bit_exact(B, orc, torch_cuda, n, variant):
     torch = torch_cuda
     L = B.load()
@@ -208,7 +208,7 @@ def random_csr(rng, rows, cols, lens):
     return a
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 100])
+@pytest.mark.parametrize("variant", [0, 6, 100])
 @pytest.mark.parametrize("kind", ["uniform5", "unbalanced", "empty_rows", "long_rows", "single", "mixed_tail"])
 def test_generic_csr_and_ellpack(B, orc, torch_cuda, kind, variant):
     """row-length variety of tests/helpers/matrix_fixtures.cpp:296-370 (random_sparse, unbalanced_rows),
@@ -287,7 +287,7 @@ def _generic_csr_and_ellpack(B, orc, torch, L, kind, variant):
         assert L.b200_spmv_ellpack(dptr(rp), dptr(va), dptr(x), dptr(y), rows, 1001, 1.0, 0.0, None) == 1
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [0, 6])
 @pytest.mark.parametrize("shift", [0, 1, 3])
 def test_generic_csr_many_groups_per_warp(B, orc, torch_cuda, variant, shift):
     """1200 x 1200 stencil through the GENERIC kernels: every persistent warp walks many 32-row groups

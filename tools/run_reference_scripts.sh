@@ -23,7 +23,7 @@ set -euo pipefail
 ROOT="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 PKG="$ROOT/cuda-spmv-benchmark_b200"
 SCRIPTS="${B200_REFERENCE_SCRIPTS:-$ROOT/oracle/_ref/scripts}"
-OUT="${1:?usage: run_reference_scripts.sh <out-dir> [run_all ...|weak ...]}"
+OUT="$(mkdir -p "${1:?usage: run_reference_scripts.sh <out-dir> [run_all ...|weak ...]}" && cd "$1" && pwd)"
 shift
 WHAT="${1:-run_all}"
 [ $# -gt 0 ] && shift
