@@ -53,7 +53,7 @@ def parse():
                          "north-star topology / the reference CLI's `cg_solver_mgpu_stencil`")
     ap.add_argument("--host-buffers", default="near", choices=["near", "torch"],
                     help="pinned host vectors: 'near' = library allocator, pages on the GPU's NUMA node; 'torch' = pin_memory()")
-    ap.add_argument("--timers-every", type=int, default=4,
+    ap.add_argument("--timers-every", type=int, default=10,
                     help="record the per-phase CUDA events (roofline.avg_launch_ms) on every K-th timed step only: an event "
                          "between two kernels keeps the second one from being scheduled under the tail of the first "
                          "(programmatic dependent launch); 1 = every step")
@@ -550,6 +550,47 @@ def run_b200(args):
                             "frac_of_900GBs": round(nb.value / (us.value * 1e-6) / 900e9, 5),
                             "how": "50 back-to-back b200_halo_push launches (peer stores + arrival word), CUDA events, slowest local rank; "
                                    "inside a solve the same stores are issued by K2r and overlap its stream"}
+    if world > 1 and not single:
+        # what the platform gives every rank when ALL ranks copy at once (the e2e solve does exactly that: every
+        # rank uploads b and x0, solves, downloads x): the floor of `e2e` on this box
+        dev_buf = torch.empty(nl, dtype=torch.float64, device="cuda")
+
+        def copy_gbs(fn):
+            best = None
+            for _ in range(2):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                t_ms = e0.elapsed_time(e1)
+                best = t_ms if best is None else min(best, t_ms)
+            t = torch.tensor([best], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # slowest rank
+            return 8.0 * nl / (float(t[0]) * 1e-3) / 1e9
+        h2d = copy_gbs(lambda: dev_buf.copy_(b_host, non_blocking=True))
+        d2h = copy_gbs(lambda: x_host.copy_(dev_buf, non_blocking=True))
+        del dev_buf
+        line["e2e"]["pcie_probe"] = {
+            "h2d_gbs_per_rank_all_ranks_copying": round(h2d, 2), "d2h_gbs_per_rank_all_ranks_copying": round(d2h, 2),
+            "floor_ms": round(ms + 16.0 * nl / h2d / 1e6 + 8.0 * nl / d2h / 1e6, 2),
+            "note": "slowest rank, pinned buffers of this run; floor = device solve + this rank's bytes at these rates. "
+                    "tools/pcie_probe.py: one GPU alone reaches ~55 GB/s either way on the same box"}
+    ref_gpu = os.path.join(ROOT, "tests", "golden", "ref_gpu_10k.json")
+    if rank == 0 and os.path.exists(ref_gpu):
+        try:  # the reference's OWN kernels (recompiled for sm_100) on a B200 at 10k x 10k, recorded by oracle/run_ref_gpu.sh
+            c = json.load(open(ref_gpu))["cases"][0]
+            line["extra"] = {"reference_gpu_b200": {
+                "grid": c["n"], "how": "oracle/_ref/{spmv_bench,cg_solver} (reference sources, -arch=sm_100) run by oracle/run_ref_gpu.sh on a B200; "
+                                       "fixture tests/golden/ref_gpu_10k.json; not the same box as this line",
+                "spmv_stencil5_csr_ms": c["spmv"]["stencil5-csr"]["execution_time_ms"],
+                "spmv_cusparse_csr_ms": c["spmv"]["cusparse-csr"]["execution_time_ms"],
+                "cg_stencil5_csr_ms_per_iteration": round(c["cg"]["stencil5-csr"]["ms_per_iteration"], 4),
+                "cg_cusparse_csr_ms_per_iteration": round(c["cg"]["cusparse-csr"]["ms_per_iteration"], 4),
+                "cg_note": "the reference CLI measures warm restarts (x is not reset): compare per iteration"}}
+        except Exception:
+            pass
     if world == 1 and not args.no_operators and not args.weak:
         op.contents.free()
         torch.cuda.empty_cache()

@@ -703,19 +703,34 @@ extern "C" int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double
     return launch_stencil_cg<ST_DOT>(band, g, (cudaStream_t)stream);
 }
 
+namespace {
+int update_xr(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r, const b200_reduce_ctx* ctx,
+              int which, b200_stream stream);
+}
 extern "C" int b200_cg_update_xr(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r,
                                  const b200_reduce_ctx* ctx, b200_stream stream) {
+    return update_xr(n, d_p, d_Ap, d_x, d_r, ctx, RED_RR, stream);
+}
+// same pass, but the r.r tail only tests convergence: beta comes from the r.z tail behind the preconditioner solve
+extern "C" int b200_pcg_update_xr_stored_z(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r,
+                                           const b200_reduce_ctx* ctx, b200_stream stream) {
+    return update_xr(n, d_p, d_Ap, d_x, d_r, ctx, RED_RRC, stream);
+}
+namespace {
+int update_xr(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r, const b200_reduce_ctx* ctx,
+              int which, b200_stream stream) {
     if (!d_p || !d_Ap || !d_x || !d_r) return fail(B200_EINVAL, "cg_update_xr: NULL argument");
     const bool v2 = aligned16(d_p) && aligned16(d_Ap) && aligned16(d_x) && aligned16(d_r);
     const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtasPerSm);
     TailArgs t;
-    int rc = make_tail(ctx, RED_RR, 0, grid, &t, "cg_update_xr");
+    int rc = make_tail(ctx, which, 0, grid, &t, "cg_update_xr");
     if (rc) return rc;
     const CGScalars* sc = static_cast<const CGScalars*>(ctx->d_scalars);
     if (v2) launch_plain(cg_update_xr_kernel<2>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_p, d_Ap, d_x, d_r, t);
     else launch_plain(cg_update_xr_kernel<1>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_p, d_Ap, d_x, d_r, t);
     return check_launch("cg_update_xr_kernel");
 }
+}  // namespace
 
 extern "C" int b200_cg_update_p(long long n, const void* d_scalars, const double* d_r, double* d_p,
                                 b200_stream stream) {
@@ -806,11 +821,23 @@ extern "C" int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, 
 }
 
 extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
-                                double* d_x, b200_stream stream) {
+                                double* d_x, int only_if_converged, b200_stream stream) {
     if (!d_scalars || !d_p0 || !d_p1 || !d_x) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
     const int grid = blas1_grid(n, 1);
-    launch_pdl(cg_finish_x_kernel, grid, 256, 0, (cudaStream_t)stream, n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x);
+    launch_pdl(cg_finish_x_kernel, grid, 256, 0, (cudaStream_t)stream, n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x,
+               only_if_converged);
     return check_launch("cg_finish_x_kernel");
+}
+
+extern "C" int b200_cg_update_px(long long n, const void* d_scalars, const double* d_r, double* d_p, double* d_x,
+                                 b200_stream stream) {
+    if (!d_scalars || !d_r || !d_p || !d_x) return fail(B200_EINVAL, "cg_update_px: NULL argument");
+    const bool v2 = aligned16(d_r) && aligned16(d_p) && aligned16(d_x);
+    const int grid = blas1_grid(n, v2 ? 2 : 1, kRrCtasPerSm);
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    if (v2) launch_plain(cg_update_px_kernel<2>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_r, d_p, d_x);
+    else launch_plain(cg_update_px_kernel<1>, grid, 256, 0, (cudaStream_t)stream, n, sc, d_r, d_p, d_x);
+    return check_launch("cg_update_px_kernel");
 }
 
 extern "C" int b200_cg_reduce(const b200_reduce_ctx* ctx, int which, int n_partials, int two_sums, int phases,
@@ -848,14 +875,14 @@ extern "C" int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, con
     return check_launch("pcg_diag_inv_kernel");
 }
 
-extern "C" int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, const b200_reduce_ctx* ctx,
-                             b200_stream stream) {
-    if (!d_r || !d_dinv || !d_p) return fail(B200_EINVAL, "pcg_init: NULL argument");
+extern "C" int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, const double* d_z, double* d_p,
+                             const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_r || (!d_dinv && !d_z) || !d_p) return fail(B200_EINVAL, "pcg_init: NULL argument");
     const int grid = blas1_grid(n, 1);
     TailArgs t;
     int rc = make_tail(ctx, RED_RZ0, 0, grid, &t, "pcg_init");
     if (rc) return rc;
-    pcg_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_r, d_dinv, d_p, t);
+    pcg_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d_r, d_dinv, d_z, d_p, t);
     return check_launch("pcg_init_kernel");
 }
 
@@ -873,7 +900,7 @@ extern "C" int b200_pcg_update_xr(long long n, const double* d_p, const double* 
 
 extern "C" int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
                                  const b200_halo_push_args* push, b200_stream stream) {
-    if (!d_scalars || !d_r || !d_dinv || !d_p) return fail(B200_EINVAL, "pcg_update_p: NULL argument");
+    if (!d_scalars || !d_r || !d_p) return fail(B200_EINVAL, "pcg_update_p: NULL argument");  // d_dinv NULL: d_r holds z
     HaloPushArgs h;
     int rc = make_push(push, n, d_p, d_scalars, &h, "pcg_update_p");
     if (rc) return rc;
@@ -882,12 +909,48 @@ extern "C" int b200_pcg_update_p(long long n, const void* d_scalars, const doubl
     return check_launch("pcg_update_p_kernel");
 }
 
-extern "C" int b200_dot_partials(long long n, const double* d_x, const double* d_y, const b200_reduce_ctx* ctx,
+namespace {
+int make_line_blocks(long long n_local, long long row_offset, int grid_size, LineBlocks* lb) {
+    if (n_local < 1 || row_offset < 0 || grid_size < 1) return fail(B200_EINVAL, "block-Jacobi: bad band");
+    lb->row_offset = row_offset; lb->n_local = n_local; lb->n = grid_size;
+    lb->first_grid_row = row_offset / grid_size;
+    const long long last = (row_offset + n_local - 1) / grid_size;
+    lb->n_blocks = (int)(last - lb->first_grid_row + 1);
+    return B200_OK;
+}
+}  // namespace
+
+extern "C" int b200_bj_factor(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
+                              long long row_offset, int grid_size, int ell_width, double* d_m, double* d_invd, double* d_c,
+                              int* d_err, b200_stream stream) {
+    if (!d_col_idx || !d_values || !d_m || !d_invd || !d_c || !d_err) return fail(B200_EINVAL, "bj_factor: NULL argument");
+    if (!d_row_ptr && ell_width < 1) return fail(B200_EINVAL, "bj_factor: ELLPACK needs a width");
+    LineBlocks lb;
+    int rc = make_line_blocks(n_local, row_offset, grid_size, &lb);
+    if (rc) return rc;
+    bj_factor_kernel<<<(lb.n_blocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lb, d_row_ptr, ell_width, d_col_idx, d_values,
+                                                                                 d_m, d_invd, d_c, d_err);
+    return check_launch("bj_factor_kernel");
+}
+
+extern "C" int b200_bj_solve(long long n_local, long long row_offset, int grid_size, const void* d_scalars, const double* d_m,
+                             const double* d_invd, const double* d_c, const double* d_r, double* d_z, b200_stream stream) {
+    if (!d_m || !d_invd || !d_c || !d_r || !d_z) return fail(B200_EINVAL, "bj_solve: NULL argument");
+    LineBlocks lb;
+    int rc = make_line_blocks(n_local, row_offset, grid_size, &lb);
+    if (rc) return rc;
+    bj_solve_kernel<<<(lb.n_blocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lb, static_cast<const CGScalars*>(d_scalars), d_m,
+                                                                                d_invd, d_c, d_r, d_z);
+    return check_launch("bj_solve_kernel");
+}
+
+extern "C" int b200_dot_partials(long long n, const double* d_x, const double* d_y, int which, const b200_reduce_ctx* ctx,
                                  b200_stream stream) {
     if (!d_x || !d_y) return fail(B200_EINVAL, "dot_partials: NULL argument");
+    if (which != RED_PAP && which != RED_RZ && which != RED_RZ0 && which != RED_SUM) return fail(B200_EINVAL, "dot_partials: bad `which`");
     const int grid = blas1_grid(n, 1);
     TailArgs t;
-    int rc = make_tail(ctx, RED_PAP, 0, grid, &t, "dot_partials");
+    int rc = make_tail(ctx, which, 0, grid, &t, "dot_partials");
     if (rc) return rc;
     dot_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, static_cast<const CGScalars*>(ctx->d_scalars), d_x, d_y, t);
     return check_launch("dot_partials_kernel");

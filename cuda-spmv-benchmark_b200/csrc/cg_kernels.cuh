@@ -94,7 +94,9 @@ struct HaloDirArgs {
     int beta_zero;
 };
 
-enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3, RED_RZ0 = 4, RED_PCG = 5 };  // 4, 5: Jacobi PCG
+// 4, 5: Jacobi PCG (z = D^-1 r formed on the fly); 6, 7: PCG with a stored z (block-Jacobi): the r.r tail only
+// tests convergence, beta comes out of the r.z tail that follows the preconditioner solve
+enum { RED_RR0 = 0, RED_PAP = 1, RED_RR = 2, RED_SUM = 3, RED_RZ0 = 4, RED_PCG = 5, RED_RRC = 6, RED_RZ = 7 };
 enum { RED_PUSH = 1, RED_COMBINE = 2 };
 #define B200_RED_GROUP 256
 
@@ -208,14 +210,6 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
     const uint64_t t_begin = globaltimer_ns();
     CGScalars* sc = a.sc;
     uint32_t* sh_seq = reinterpret_cast<uint32_t*>(sh + 2 * B200_MAX_RANKS);
-    if (a.publish && t == 0) {
-        // every CTA fenced its peer stores (system scope) before it took its ticket
-        const uint32_t hs = a.my_xchg->halo_seq + 1u;
-        a.my_xchg->halo_seq = hs;
-        __threadfence_system();
-        if (a.flag_prev != nullptr) st_release_sys(a.flag_prev, hs);
-        if (a.flag_next != nullptr) st_release_sys(a.flag_next, hs);
-    }
     if (a.world > 1) {
         if (t == 0) {
             uint32_t seq = a.my_xchg->red_seq;
@@ -227,6 +221,8 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
     const uint32_t seq = (a.world > 1) ? *sh_seq : 0u;
     if (a.phases & RED_PUSH) {
         if (t == 0 && !(a.phases & RED_COMBINE)) { a.stash[0] = total; a.stash[1] = total_b; }
+        // the scalar goes out FIRST: the peers' tails are waiting for it, while the halo sequence number
+        // below is only looked at by their next kernel
         if (a.world > 1 && t < a.world) {
             const uint64_t tag = (uint64_t)seq << 32;
             uint64_t* dst = a.peer_xchg[t]->slots[seq & 1][a.rank];
@@ -239,6 +235,16 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
                 st_volatile_u64(dst + 3, tag | (bits_b >> 32));
             }
         }
+    }
+    if (a.publish && t == 32 % blockDim.x) {
+        // every CTA fenced its peer stores (system scope) before it took its ticket, and this CTA saw all the
+        // tickets: ONE system fence orders those stores before both arrival words.  Done by a lane outside
+        // the warp that exchanges the scalars, so it overlaps the wait below.
+        const uint32_t hs = a.my_xchg->halo_seq + 1u;
+        a.my_xchg->halo_seq = hs;
+        __threadfence_system();
+        if (a.flag_prev != nullptr) st_relaxed_sys(a.flag_prev, hs);
+        if (a.flag_next != nullptr) st_relaxed_sys(a.flag_next, hs);
     }
     if (!(a.phases & RED_COMBINE)) return;
     if (a.world > 1) {
@@ -283,7 +289,10 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
         sc->alpha = sc->rr_old / total;  // PCG keeps rho = r.z in rr_old
     } else if (a.which == RED_RZ0) {
         sc->rr_old = total;  // rho_0 = r0.z0 (b_norm was set by RED_RR0)
-    } else {  // RED_RR, RED_PCG (total = r.r, total_b = r.z)
+    } else if (a.which == RED_RZ) {
+        sc->beta = total / sc->rr_old;  // rho_new / rho
+        sc->rr_old = total;
+    } else {  // RED_RR, RED_PCG (total = r.r, total_b = r.z), RED_RRC (convergence test only)
         sc->rr_new = total;
         const double res = sqrt(total);
         sc->residual = res;
@@ -295,7 +304,7 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
         } else if (a.which == RED_PCG) {
             sc->beta = total_b / sc->rr_old;
             sc->rr_old = total_b;
-        } else {
+        } else if (a.which == RED_RR) {
             sc->beta = total / sc->rr_old;
             sc->rr_old = total;
         }
@@ -466,10 +475,11 @@ __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGS
     constexpr int UNROLL = 4;
     const long long tile = 256LL * VEC * UNROLL;
     const long long next_lo = n - h.halo;
+    bool pushed = false;
     auto push = [&](long long i, double v) {
         if (PUSH) {
-            if (h.dst_prev != nullptr && i < h.halo) h.dst_prev[i] = v;
-            if (h.dst_next != nullptr && i >= next_lo) h.dst_next[i - next_lo] = v;
+            if (h.dst_prev != nullptr && i < h.halo) { h.dst_prev[i] = v; pushed = true; }
+            if (h.dst_next != nullptr && i >= next_lo) { h.dst_next[i - next_lo] = v; pushed = true; }
         }
     };
     double acc = 0.0;
@@ -519,8 +529,9 @@ __global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGS
     }
     griddep_launch();
     // the edge stores must be visible system-wide before this CTA's ticket: the CTA that ends up with
-    // the total publishes the halo sequence number to the neighbours (cg_tail)
-    if (PUSH) __threadfence_system();
+    // the total publishes the halo sequence number to the neighbours (cg_tail).  Only the threads that
+    // stored to a peer pay for the fence (a handful of CTAs at the two ends of the band).
+    if (PUSH && pushed) __threadfence_system();
     acc = block_sum(acc, scratch);  // contains a __syncthreads
     B200_TAIL_FINISH(tail, acc, 0.0);
 }
@@ -555,12 +566,16 @@ __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
 
 // After the last iteration of the deferred-x schedule x still lacks alpha_last * p_last.
 // p_last lives in p0 or p1 depending on the parity of the completed iterations (known on the device).
+// only_if_converged: the K3x schedule (below) retires x inside the p update of the same iteration, so an
+// update is pending only when the convergence test stopped the loop in front of that kernel.
 __global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGScalars* __restrict__ sc,
                                                           const double* __restrict__ p0,
-                                                          const double* __restrict__ p1, double* __restrict__ x) {
+                                                          const double* __restrict__ p1, double* __restrict__ x,
+                                                          int only_if_converged) {
     griddep_wait();
     const int it = sc->iterations;
     if (it <= 0) return;
+    if (only_if_converged && !sc->converged) return;
     const double alpha = sc->alpha;
     const double* __restrict__ p = ((it - 1) & 1) ? p1 : p0;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
@@ -611,6 +626,65 @@ __global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGS
     }
 }
 
+// K3x: p = r + beta p AND x += alpha p_old in one pass (operators without a fused SpMV: K2 shrinks to K2r,
+// 24 B/row, and this kernel moves 40 B/row instead of K3's 24 -- 64 instead of 72 B/row for the BLAS-1
+// part of an iteration).  Same fma's as K2 / K3 (cg_solver.cu:59-66,91-96), so the iterates are
+// bit-identical to the classic schedule.  alpha is still the alpha of this iteration: the next p.Ap tail
+// has not run yet.
+template <int VEC>
+__global__ void __launch_bounds__(256) cg_update_px_kernel(long long n, const CGScalars* __restrict__ sc,
+                                                           const double* __restrict__ r, double* __restrict__ p,
+                                                           double* __restrict__ x) {
+    griddep_wait();
+    if (sc->converged) return;
+    const double alpha = sc->alpha, beta = sc->beta;
+    constexpr int UNROLL = 4;
+    const long long tile = 256LL * VEC * UNROLL;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        if (VEC == 2) {
+            double2 pv[UNROLL], rv[UNROLL], xv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    pv[u] = __ldcs(reinterpret_cast<const double2*>(p + i));
+                    rv[u] = __ldcs(reinterpret_cast<const double2*>(r + i));
+                    xv[u] = __ldcs(reinterpret_cast<const double2*>(x + i));
+                } else if (i < n) {
+                    pv[u] = make_double2(p[i], 0.0);
+                    rv[u] = make_double2(r[i], 0.0);
+                    xv[u] = make_double2(x[i], 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + ((long long)u * 256 + threadIdx.x) * 2;
+                if (i + 1 < n) {
+                    xv[u].x = fma(alpha, pv[u].x, xv[u].x);
+                    xv[u].y = fma(alpha, pv[u].y, xv[u].y);
+                    pv[u].x = fma(beta, pv[u].x, rv[u].x);
+                    pv[u].y = fma(beta, pv[u].y, rv[u].y);
+                    *reinterpret_cast<double2*>(x + i) = xv[u];
+                    *reinterpret_cast<double2*>(p + i) = pv[u];
+                } else if (i < n) {
+                    x[i] = fma(alpha, pv[u].x, xv[u].x);
+                    p[i] = fma(beta, pv[u].x, rv[u].x);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const long long i = base + (long long)u * 256 + threadIdx.x;
+                if (i < n) {
+                    const double po = p[i];
+                    x[i] = fma(alpha, po, x[i]);
+                    p[i] = fma(beta, po, r[i]);
+                }
+            }
+        }
+    }
+}
+
 // ---- Jacobi-preconditioned CG (not in the reference: its README lists preconditioning as the next step) ----
 // z = D^-1 r is never stored: K2p forms it for the r.z partials, K3p forms it again for p = z + beta p.
 // dinv[i] = 1 / A(i,i) from the CSR / ELLPACK arrays (row_ptr == NULL: ELLPACK of width `width`);
@@ -632,9 +706,10 @@ __global__ void __launch_bounds__(256) pcg_diag_inv_kernel(long long n_local, lo
 }
 
 // after the residual init (r = b - A x0): p0 = z0 = dinv r0, partials of rho_0 = r0.z0
+// dinv == NULL: z = zin (already solved, block-Jacobi)
 __global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double* __restrict__ r,
-                                                       const double* __restrict__ dinv, double* __restrict__ p,
-                                                       const TailArgs tail) {
+                                                       const double* __restrict__ dinv, const double* __restrict__ zin,
+                                                       double* __restrict__ p, const TailArgs tail) {
     __shared__ double scratch[8];
     B200_TAIL_SHARED;
     double acc = 0.0;
@@ -644,7 +719,7 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double
         for (int u = 0; u < 4; u++) {
             const long long i = base + u * 256 + threadIdx.x;
             if (i < n) {
-                const double rv = r[i], z = dinv[i] * rv;
+                const double rv = r[i], z = dinv ? dinv[i] * rv : zin[i];
                 p[i] = z;
                 acc = fma(rv, z, acc);
             }
@@ -708,13 +783,14 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CG
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const long long i = base + u * 256 + threadIdx.x;
-            if (i < n) { pv[u] = __ldcs(p + i); rv[u] = __ldcs(r + i); dv[u] = __ldcs(dinv + i); }
+            if (i < n) { pv[u] = __ldcs(p + i); rv[u] = __ldcs(r + i); dv[u] = dinv ? __ldcs(dinv + i) : 1.0; }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const long long i = base + u * 256 + threadIdx.x;
             if (i < n) {
-                const double v = fma(beta, pv[u], dv[u] * rv[u]);
+                // dinv == NULL: `r` already holds z = M^-1 r (block-Jacobi)
+                const double v = fma(beta, pv[u], dinv ? dv[u] * rv[u] : rv[u]);
                 p[i] = v;
                 if (push) {
                     if (h.dst_prev != nullptr && i < h.halo) h.dst_prev[i] = v;
@@ -736,6 +812,85 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CG
             if (h.dst_prev != nullptr) st_release_sys(h.flag_prev, seq);
             if (h.dst_next != nullptr) st_release_sys(h.flag_next, seq);
         }
+    }
+}
+
+// ---- block-Jacobi preconditioner with line blocks ------------------------------------------------------
+// M = the tridiagonal part of A inside every grid row (W, C, E of the 5-point stencil), i.e. one n x n
+// tridiagonal block per grid row, clipped to the rank's band.  z = M^-1 r is one Thomas solve per block.
+// One thread per block, marching along the row: neighbouring threads work on neighbouring grid rows, their
+// accesses are n elements apart, and the four consecutive elements of a 32-byte sector are consumed by the
+// same thread in its next steps (L1 hit).  Set-up (untimed, once per solve): the forward elimination of the
+// matrix, m_j = a_j / d'_{j-1}, d'_j = d_j - m_j c_{j-1}, stored as m[], 1 / d'[] and c[].
+struct LineBlocks {
+    long long row_offset, n_local;
+    int n;              // grid side
+    long long first_grid_row;  // grid row of block 0
+    int n_blocks;
+};
+__device__ __forceinline__ void line_block_range(const LineBlocks& lb, int b, long long* lo, long long* hi) {
+    const long long gr = lb.first_grid_row + b;
+    long long s = gr * lb.n, e = s + lb.n;
+    if (s < lb.row_offset) s = lb.row_offset;
+    if (e > lb.row_offset + lb.n_local) e = lb.row_offset + lb.n_local;
+    *lo = s - lb.row_offset;  // local rows [lo, hi)
+    *hi = e - lb.row_offset;
+}
+
+// coefficient of column `want` in local row lr (CSR: row_ptr != NULL; ELLPACK of `width` otherwise); 0 if absent
+__device__ __forceinline__ double row_coeff(const int* row_ptr, const int* col_idx, const double* values, int width,
+                                            long long lr, long long want) {
+    const long long s = row_ptr ? row_ptr[lr] : lr * width, e = row_ptr ? row_ptr[lr + 1] : (lr + 1) * width;
+    double v = 0.0;
+    for (long long k = s; k < e; k++)
+        if ((unsigned int)col_idx[k] == (unsigned int)want && (row_ptr || col_idx[k] >= 0)) v = values[k];
+    return v;
+}
+
+__global__ void __launch_bounds__(128) bj_factor_kernel(const LineBlocks lb, const int* __restrict__ row_ptr, int width,
+                                                        const int* __restrict__ col_idx, const double* __restrict__ values,
+                                                        double* __restrict__ m, double* __restrict__ invd,
+                                                        double* __restrict__ c, int* __restrict__ err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= lb.n_blocks) return;
+    long long lo, hi;
+    line_block_range(lb, b, &lo, &hi);
+    double dprev = 1.0, cprev = 0.0;
+    for (long long lr = lo; lr < hi; lr++) {
+        const long long r = lb.row_offset + lr;
+        const double d = row_coeff(row_ptr, col_idx, values, width, lr, r);
+        const double a = lr > lo ? row_coeff(row_ptr, col_idx, values, width, lr, r - 1) : 0.0;
+        const double cc = lr + 1 < hi ? row_coeff(row_ptr, col_idx, values, width, lr, r + 1) : 0.0;
+        const double mj = lr > lo ? a / dprev : 0.0;
+        const double dj = fma(-mj, cprev, d);
+        if (dj == 0.0 || d == 0.0) *err = 1;
+        m[lr] = mj;
+        invd[lr] = 1.0 / dj;
+        c[lr] = cc;
+        dprev = dj;
+        cprev = cc;
+    }
+}
+
+// z = M^-1 r: forward y_j = r_j - m_j y_{j-1}, backward z_j = (y_j - c_j z_{j+1}) / d'_j  (y kept in z)
+__global__ void __launch_bounds__(128) bj_solve_kernel(const LineBlocks lb, const CGScalars* __restrict__ sc,
+                                                       const double* __restrict__ m, const double* __restrict__ invd,
+                                                       const double* __restrict__ c, const double* __restrict__ r,
+                                                       double* __restrict__ z) {
+    if (sc != nullptr && sc->converged) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= lb.n_blocks) return;
+    long long lo, hi;
+    line_block_range(lb, b, &lo, &hi);
+    double y = 0.0;
+    for (long long lr = lo; lr < hi; lr++) {
+        y = fma(-m[lr], y, r[lr]);
+        z[lr] = y;
+    }
+    double zn = 0.0;
+    for (long long lr = hi - 1; lr >= lo; lr--) {
+        zn = fma(-c[lr], zn, z[lr]) * invd[lr];
+        z[lr] = zn;
     }
 }
 

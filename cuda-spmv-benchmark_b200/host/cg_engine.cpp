@@ -501,6 +501,8 @@ struct Engine {
             if (combine(B200_RED_RZ0, 0)) return 1;
         }
         const bool dx = fused && schedule_deferred_x() && !pcg;
+        // operators without a fused SpMV: same idea one level down -- x is retired inside the p update (K3x)
+        const bool px = !fused && schedule_deferred_x() && !pcg;
         if (multi) {
             B200_K(b200_halo_push(w.p, w.nl, &push, nullptr, w.st));
             if (!team.phase()) return 1;
@@ -557,10 +559,10 @@ struct Engine {
                 mark(T_RED_PAP, it);
             }
             nvtxRangePushA("BLAS_AXPY");
-            if (dx) {
+            if (dx || px) {
                 // K2r: r -= alpha Ap, r.r -> convergence, beta; multi-GPU: the edges of the new r go straight
                 // into the neighbours' landing buffers
-                B200_K(b200_cg_update_r(w.nl, w.Ap, w.r, multi ? &push : nullptr, &ctx, w.st));
+                B200_K(b200_cg_update_r(w.nl, w.Ap, w.r, (dx && multi) ? &push : nullptr, &ctx, w.st));
             } else if (pcg) {  // K2p: + r.z with z = D^-1 r
                 B200_K(b200_pcg_update_xr(w.nl, w.p, w.Ap, w.dinv, w.x, w.r, &ctx, w.st));
             } else {  // K2: x += alpha p, r -= alpha Ap, r.r
@@ -587,6 +589,7 @@ struct Engine {
             if (!dx) {
                 Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
                 if (pcg) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, multi ? &push : nullptr, w.st));  // K3p
+                else if (px) B200_K(b200_cg_update_px(w.nl, w.scalars, w.r, w.p, w.x, w.st));                      // K3x
                 else if (!multi) B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));                        // K3
                 else B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, &push, w.st));  // K3 + halo push
                 if (multi && !team.phase()) return 1;
@@ -615,7 +618,11 @@ struct Engine {
         }
         if (dx) {
             // the x update of the last completed iteration is still pending: x += alpha p_last
-            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, w.st));
+            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, 0, w.st));
+            mark(T_P);
+        } else if (px) {
+            // pending only if the convergence test stopped the loop in front of K3x
+            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p, w.x, 1, w.st));
             mark(T_P);
         }
         B200_CUDA(cudaEventRecord(w.ev1, w.st));

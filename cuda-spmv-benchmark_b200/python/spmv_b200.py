@@ -117,10 +117,10 @@ C_SYMBOLS = [
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_halo_dir",
-    "b200_cg_finish_x", "b200_cg_set_schedule", "b200_cg_set_pdl", "b200_cg_read_tail_times",
+    "b200_cg_finish_x", "b200_cg_update_px", "b200_cg_set_schedule", "b200_cg_set_pdl", "b200_cg_read_tail_times",
     "b200_csr_dot_partials_capacity",
     "b200_spmv_csr_dot", "b200_spmv_ellpack_dot", "b200_pcg_diag_inv", "b200_pcg_init", "b200_pcg_update_xr",
-    "b200_pcg_update_p",
+    "b200_pcg_update_p", "b200_bj_factor", "b200_bj_solve", "b200_pcg_update_xr_stored_z",
     "b200_dot_partials", "b200_residual_init_generic", "b200_checksum", "b200_halo_push",
     "b200_xchg_flag_prev_offset", "b200_xchg_flag_next_offset", "b200_xchg_halo_seq_offset", "b200_stencil5_nnz_before",
     "b200_gen_stencil5_csr", "b200_gen_stencil5_ellpack", "b200_gen_stencil5_entries", "b200_fill",
@@ -212,16 +212,20 @@ def load():
     L.b200_cg_spmv_fused.argtypes = [C.POINTER(Band), vp, vp, vp, vp, vp, ctx, vp]
     L.b200_cg_update_r.argtypes = [ll, vp, vp, push, ctx, vp]
     L.b200_cg_halo_dir.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp]
-    L.b200_cg_finish_x.argtypes = [ll, vp, vp, vp, vp, vp]
+    L.b200_cg_finish_x.argtypes = [ll, vp, vp, vp, vp, i32, vp]
+    L.b200_cg_update_px.argtypes = [ll, vp, vp, vp, vp, vp]
     L.b200_cg_set_schedule.restype = None
     L.b200_cg_set_schedule.argtypes = [i32]
     L.b200_cg_read_tail_times.argtypes = [vp, C.POINTER(TailTimes), vp]
-    L.b200_dot_partials.argtypes = [ll, vp, vp, ctx, vp]
+    L.b200_dot_partials.argtypes = [ll, vp, vp, i32, ctx, vp]
     L.b200_residual_init_generic.argtypes = [ll, vp, vp, vp, vp, ctx, vp]
     L.b200_checksum.argtypes = [ll, vp, ctx, vp]
     L.b200_halo_push.argtypes = [vp, ll, push, vp, vp]
     L.b200_pcg_diag_inv.argtypes = [vp, vp, vp, ll, ll, i32, vp, vp, vp]
-    L.b200_pcg_init.argtypes = [ll, vp, vp, vp, ctx, vp]
+    L.b200_pcg_init.argtypes = [ll, vp, vp, vp, vp, ctx, vp]
+    L.b200_bj_factor.argtypes = [vp, vp, vp, ll, ll, i32, i32, vp, vp, vp, vp, vp]
+    L.b200_bj_solve.argtypes = [ll, ll, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.b200_pcg_update_xr_stored_z.argtypes = [ll, vp, vp, vp, vp, ctx, vp]
     L.b200_pcg_update_xr.argtypes = [ll, vp, vp, vp, vp, vp, ctx, vp]
     L.b200_pcg_update_p.argtypes = [ll, vp, vp, vp, vp, push, vp]
     L.b200_stencil5_nnz_before.restype = ll

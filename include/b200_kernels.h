@@ -178,7 +178,8 @@ typedef struct {
 
 /* which: 0 = r0.r0 (sets rr_old, b_norm), 1 = p.Ap (alpha), 2 = r.r (convergence test, beta,
  * iteration count), 3 = plain sum(s) into d_out, 4 = PCG rho_0, 5 = PCG r.r + r.z */
-enum { B200_RED_RR0 = 0, B200_RED_PAP = 1, B200_RED_RR = 2, B200_RED_SUM = 3, B200_RED_RZ0 = 4, B200_RED_PCG = 5 };
+enum { B200_RED_RR0 = 0, B200_RED_PAP = 1, B200_RED_RR = 2, B200_RED_SUM = 3, B200_RED_RZ0 = 4, B200_RED_PCG = 5,
+       B200_RED_RRC = 6 /* r.r: convergence test only */, B200_RED_RZ = 7 /* r.z: beta = rho_new / rho */ };
 
 size_t b200_cg_scalars_bytes(void);
 size_t b200_cg_status_bytes(void);
@@ -221,7 +222,7 @@ int b200_cg_reduce(const b200_reduce_ctx* ctx, int which, int n_partials, int tw
                    b200_stream stream);
 
 /* generic helpers for operators without a fused entry point */
-int b200_dot_partials(long long n, const double* d_x, const double* d_y, const b200_reduce_ctx* ctx,
+int b200_dot_partials(long long n, const double* d_x, const double* d_y, int which, const b200_reduce_ctx* ctx,
                       b200_stream stream);
 int b200_residual_init_generic(long long n, const double* d_b, const double* d_Ap, double* d_r,
                                double* d_p, const b200_reduce_ctx* ctx, b200_stream stream);
@@ -259,7 +260,12 @@ int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const doubl
                      const uint32_t* d_flag_prev, const uint32_t* d_flag_next, const void* d_my_xchg,
                      void* d_scalars, int beta_zero, b200_stream stream);
 int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
-                     double* d_x, b200_stream stream);
+                     double* d_x, int only_if_converged, b200_stream stream);
+/* K3x, for operators without a fused SpMV: p = r + beta p and x += alpha p_old in one pass, so that K2
+ * shrinks to b200_cg_update_r (64 instead of 72 B/row of BLAS-1 traffic per iteration; update_p_kernel
+ * :91-96 + axpy_kernel_device :59-66).  b200_cg_finish_x(only_if_converged = 1) closes the solve. */
+int b200_cg_update_px(long long n, const void* d_scalars, const double* d_r, double* d_p, double* d_x,
+                      b200_stream stream);
 /* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 3-launch schedule;
  * the environment variable B200_CG_SCHEDULE=classic selects 0 at start-up */
 void b200_cg_set_schedule(int deferred_x);
@@ -280,13 +286,25 @@ int b200_cg_read_tail_times(const void* d_scalars, b200_cg_tail_times* h_out, b2
  * serves unchanged.  Multi-GPU: K3p pushes the edges of the new p like b200_cg_update_p_push. */
 int b200_pcg_diag_inv(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
                       long long row_offset, int ell_width, double* d_dinv, int* d_err, b200_stream stream);
-/* p0 = z0 = D^-1 r0 ; r0.z0 -> rho_0 */
-int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, double* d_p, const b200_reduce_ctx* ctx,
-                  b200_stream stream);
+/* p0 = z0 ; r0.z0 -> rho_0, with z0 = D^-1 r0 (d_dinv) or an already solved z0 (d_dinv NULL, d_z: block-Jacobi) */
+int b200_pcg_init(long long n, const double* d_r, const double* d_dinv, const double* d_z, double* d_p,
+                  const b200_reduce_ctx* ctx, b200_stream stream);
 /* K2p: x += alpha p ; r -= alpha Ap ; r.r -> convergence ; r.z -> beta, rho */
 int b200_pcg_update_xr(long long n, const double* d_p, const double* d_Ap, const double* d_dinv, double* d_x,
                        double* d_r, const b200_reduce_ctx* ctx, b200_stream stream);
-/* K3p: p = D^-1 r + beta p (push != NULL: + halo push) */
+/* Block-Jacobi with line blocks: M = the W / C / E part of A inside every grid row (one tridiagonal block per
+ * grid row, clipped to the band); z = M^-1 r by the Thomas algorithm, one thread per block.  b200_bj_factor
+ * (once per solve) stores the forward elimination of the matrix, b200_bj_solve applies it.  The iteration is
+ * K1 -> b200_pcg_update_xr_stored_z (r.r: convergence only) -> b200_bj_solve -> b200_dot_partials(r, z,
+ * B200_RED_RZ) -> b200_pcg_update_p(d_dinv = NULL, d_r = z). */
+int b200_bj_factor(const int* d_row_ptr, const int* d_col_idx, const double* d_values, long long n_local,
+                   long long row_offset, int grid_size, int ell_width, double* d_m, double* d_invd, double* d_c,
+                   int* d_err, b200_stream stream);
+int b200_bj_solve(long long n_local, long long row_offset, int grid_size, const void* d_scalars, const double* d_m,
+                  const double* d_invd, const double* d_c, const double* d_r, double* d_z, b200_stream stream);
+int b200_pcg_update_xr_stored_z(long long n, const double* d_p, const double* d_Ap, double* d_x, double* d_r,
+                                const b200_reduce_ctx* ctx, b200_stream stream);
+/* K3p: p = D^-1 r + beta p (push != NULL: + halo push); d_dinv NULL: d_r already holds z */
 int b200_pcg_update_p(long long n, const void* d_scalars, const double* d_r, const double* d_dinv, double* d_p,
                       const b200_halo_push_args* push, b200_stream stream);
 /* offsets of the halo arrival words / the halo sequence counter inside an exchange area */

@@ -200,6 +200,33 @@ def test_halo_mgpu_operator(B, orc, torch_cuda):
         del os.environ["B200_GPUS"]
 
 
+@pytest.mark.parametrize("opname", [b"cusparse-csr", b"ellpack"])
+@pytest.mark.parametrize("n", [3, 81, 300])
+@pytest.mark.parametrize("max_iters", [1000, 1, 4])
+def test_cg_k3x_schedule_bit_identical_to_classic_generic_operators(B, torch_cuda, n, max_iters, opname):
+    """operators without a fused SpMV: K1 / K2r / K3x (x retired inside the p update) must reproduce the
+    classic K1 / K2 / K3 grouping bit for bit, also when max_iters cuts the solve (no pending x update then)
+    and when the convergence test does (one pending update, applied by cg_finish_x)"""
+    L = B.load()
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(n)
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    out = []
+    try:
+        for sched in (0, 1):
+            L.b200_cg_set_schedule(sched)
+            x, st, op = solve_device(B, opname, hm, b, x0, max_iters=max_iters)
+            out.append((x, st))
+            op.contents.free()
+    finally:
+        L.b200_cg_set_schedule(1)
+    (xc, sc), (xd, sd) = out
+    assert sc["iterations"] == sd["iterations"] and sc["converged"] == sd["converged"]
+    assert sc["residual_norm"] == sd["residual_norm"]
+    assert np.array_equal(xc, xd)
+
+
 @pytest.mark.parametrize("n", [3, 64, 81, 130, 700])
 @pytest.mark.parametrize("max_iters", [1000, 1, 2, 5])
 def test_cg_deferred_x_schedule_bit_identical_to_classic(B, torch_cuda, n, max_iters):

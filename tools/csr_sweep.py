@@ -21,15 +21,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cuda-spmv-benchmark_b200", "python"))
 
 
-def build(torch, lens, cols, seed):
-    """CSR with the given row lengths; columns uniform in [0, cols), sorted inside a row"""
+def build(torch, lens, cols, seed, band=0):
+    """CSR with the given row lengths; columns uniform in [0, cols) -- or, band > 0, within +-band of the
+    row (the locality of a discretised PDE) -- sorted inside a row"""
     g = torch.Generator(device="cuda")
     g.manual_seed(seed)
     rp = torch.zeros(lens.numel() + 1, dtype=torch.int64, device="cuda")
     torch.cumsum(lens, 0, out=rp[1:])
     nnz = int(rp[-1])
     row_of = torch.repeat_interleave(torch.arange(lens.numel(), device="cuda"), lens)
-    ci = torch.randint(0, cols, (nnz,), device="cuda", generator=g, dtype=torch.int64)
+    if band > 0:
+        ci = (row_of + torch.randint(-band, band + 1, (nnz,), device="cuda", generator=g, dtype=torch.int64)).clamp_(0, cols - 1)
+    else:
+        ci = torch.randint(0, cols, (nnz,), device="cuda", generator=g, dtype=torch.int64)
     key = row_of * cols + ci
     key, _ = torch.sort(key)
     ci = (key % cols).to(torch.int32)
@@ -49,6 +53,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--long", type=int, default=200)
+    ap.add_argument("--band", type=int, default=0, help="columns within +-band of the row instead of uniform over all columns")
     ap.add_argument("--variants", default="0,6")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "csr_sweep.json"))
     a = ap.parse_args()
@@ -63,7 +68,8 @@ def main():
     s = torch.cuda.current_stream().cuda_stream
     dp = lambda t: C.c_void_p(t.data_ptr())
     N = a.rows
-    res = {"rows": N, "peak_gbs": peak, "cases": []}
+    res = {"rows": N, "peak_gbs": peak, "columns": ("within +-%d of the row" % a.band) if a.band else "uniform over all columns",
+           "cases": []}
 
     def timed(fn, warm=5, reps=10):
         for _ in range(warm):
@@ -89,7 +95,7 @@ def main():
             continue
         N = lens.numel()
         x = torch.rand(N, dtype=torch.float64, device="cuda")
-        rp, ci, va, nnz = build(torch, lens, N, 7)
+        rp, ci, va, nnz = build(torch, lens, N, 7, a.band)
         # pad the arrays by two entries (the bulk copies move 16-byte granules)
         ci = torch.cat([ci, torch.zeros(2, dtype=torch.int32, device="cuda")])
         va = torch.cat([va, torch.zeros(2, dtype=torch.float64, device="cuda")])
