@@ -17,6 +17,7 @@ extern "C" int b200_mgpu_world(void);
 extern "C" int b200_load_matrix_market_device(const char* filename, MatrixData* meta, void** d_entries_out);
 extern "C" int b200_operator_init_device_coo(SpmvOperator* op, const MatrixData* meta, const void* d_entries);
 extern "C" void b200_free_device(void* d_ptr);
+extern "C" int b200_pcg_set_preconditioner(int kind);
 
 struct CliArgs {
     std::string matrix;                 // .mtx path ("" with --grid)
@@ -27,7 +28,7 @@ struct CliArgs {
     double tol = 1e-6;
     int maxiter = 1000;
     bool timers = false, host = false;
-    bool jacobi = false;                // --precond=jacobi (extension)
+    bool jacobi = false;                // --precond=jacobi | --precond=block-jacobi (extension: preconditioned CG)
     bool device_ingest = false;         // --device-ingest: parse the .mtx and build the CSR on the GPU (extension)
     int runs = 10;
 };
@@ -56,7 +57,8 @@ inline CliArgs parse_cli(int argc, char** argv) {
         else if (starts(s, "--runs=")) a.runs = atoi(s + 7);
         else if (!strcmp(s, "--timers")) a.timers = true;
         else if (!strcmp(s, "--host")) a.host = true;
-        else if (!strcmp(s, "--precond=jacobi")) a.jacobi = true;
+        else if (!strcmp(s, "--precond=jacobi")) { a.jacobi = true; b200_pcg_set_preconditioner(1); }
+        else if (!strcmp(s, "--precond=block-jacobi")) { a.jacobi = true; b200_pcg_set_preconditioner(2); }
         else if (!strcmp(s, "--device-ingest")) a.device_ingest = true;
         else if (s[0] != '-' && a.matrix.empty()) a.matrix = s;
     }

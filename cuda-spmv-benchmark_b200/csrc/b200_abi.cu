@@ -17,7 +17,7 @@
 #include "stencil_layout.h"
 
 #ifndef B200_PLAIN_VARIANT_DEFAULT
-#define B200_PLAIN_VARIANT_DEFAULT 0
+#define B200_PLAIN_VARIANT_DEFAULT 20
 #endif
 #ifndef B200_PDL_DEFAULT
 #define B200_PDL_DEFAULT 3
@@ -260,7 +260,7 @@ int launch_direct(const b200_band* b, const Geometry& g, cudaStream_t s) {
     else stencil5_direct_kernel<ROWS, false><<<(unsigned)blocks, 256, 0, s>>>(g.a);
     return check_launch("stencil5_direct_kernel");
 }
-std::atomic<int> g_plain_variant{B200_PLAIN_VARIANT_DEFAULT};
+std::atomic<int> g_plain_variant{-1};
 }  // namespace
 
 // variant used by b200_stencil5_spmv when the band asks for the default (0): 0 = bulk-copy ring, 20..22 = sweep
@@ -273,7 +273,14 @@ extern "C" int b200_stencil5_spmv(const b200_band* band, const double* d_x, doub
     if (!d_y) return fail(B200_EINVAL, "stencil5: NULL y");
     g.a.y = d_y;
     int v = band->variant;
-    if (v == 0) v = g_plain_variant.load(std::memory_order_relaxed);
+    if (v == 0) {
+        v = g_plain_variant.load(std::memory_order_relaxed);
+        if (v < 0) {  // first use: B200_PLAIN_VARIANT overrides the built-in default
+            const char* e = getenv("B200_PLAIN_VARIANT");
+            v = e ? atoi(e) : B200_PLAIN_VARIANT_DEFAULT;
+            g_plain_variant.store(v, std::memory_order_relaxed);
+        }
+    }
     // the sweep form has no flag waits: bands whose halos are still in flight stay on the ring kernel
     if (v >= 20 && v <= 22 && !band->d_flag_prev && !band->d_flag_next) {
         if (v == 20) return launch_direct<1>(band, g, (cudaStream_t)stream);

@@ -24,28 +24,45 @@ namespace b200 {
 
 template <int ROWS, bool CG_LOADS>
 __global__ void __launch_bounds__(256) stencil5_direct_kernel(const Stencil5Args a) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long lr0 = t * ROWS;  // first local row of this thread
-    if (lr0 >= a.n_local) return;
-    const long long n = a.n;
-    const long long r0 = a.row_offset + lr0;
-    const long long i = r0 / n;
-    const long long j0 = r0 - i * n;
+    // 32-bit index arithmetic wherever a band allows it (a band has < 2^31 / 5 rows): one thread per row leaves
+    // ~9 issue slots per byte-time, a 64-bit division alone would eat most of them
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nloc = (unsigned int)a.n_local, n = (unsigned int)a.n;
+    const unsigned int lr0 = t * ROWS;  // first local row of this thread
+    if (lr0 >= nloc) return;
+    // grid coordinates of local row 0 (64-bit once per thread, cheap: constant operands), then 32-bit
+    const unsigned int i_off = (unsigned int)(a.row_offset / a.n), j_off = (unsigned int)(a.row_offset - (long long)i_off * a.n);
+    const unsigned int q = (j_off + lr0) / n;
+    const unsigned int i = i_off + q, j0 = j_off + lr0 - q * n;
     // fast path: all ROWS rows are interior points of the same grid row and lie inside the band
-    const bool fast = (i >= 1) && (i <= n - 2) && (j0 >= 1) && (j0 + ROWS - 1 <= n - 2) && (lr0 + ROWS <= a.n_local);
+    const bool fast = (i >= 1) && (i + 2 <= n) && (j0 >= 1) && (j0 + ROWS + 1 <= n) && (lr0 + ROWS <= nloc);
     if (fast) {
-        const double* v = a.values + (a.base0 + i * a.row_stride + 5 * j0);
+        const double* v = a.values + (a.base0 + (long long)i * a.row_stride + 5 * (long long)j0);
         double c[5 * ROWS];
+        // read-only path WITH L1 allocation: a thread's 40-byte run shares its 32-byte sectors with its neighbours'
+        // runs, and the five loads of a warp cover the same 1280 contiguous bytes -- streaming loads (ld.cs)
+        // would pull every sector from L2 several times
 #pragma unroll
-        for (int k = 0; k < 5 * ROWS; k++) c[k] = __ldcs(v + k);
+        for (int k = 0; k < 5 * ROWS; k++) c[k] = __ldg(v + k);
         // x(i, j0-1 .. j0+ROWS): one more than the rows on either side
         double xc[ROWS + 2], xn[ROWS], xs[ROWS];
+        if (lr0 >= n && lr0 + ROWS + n <= nloc) {  // every neighbour is a local element: plain loads
+            const double* xp = a.x + lr0;
 #pragma unroll
-        for (int k = 0; k < ROWS + 2; k++) xc[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 - 1 + k);
+            for (int k = 0; k < ROWS + 2; k++) xc[k] = __ldg(xp - 1 + k);
 #pragma unroll
-        for (int k = 0; k < ROWS; k++) {
-            xn[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 + k - n);
-            xs[k] = x_at<ST_PLAIN, CG_LOADS>(a, lr0 + k + n);
+            for (int k = 0; k < ROWS; k++) {
+                xn[k] = __ldg(xp + k - (long long)n);
+                xs[k] = __ldg(xp + k + n);
+            }
+        } else {  // first / last grid rows of a band: halo addressing
+#pragma unroll
+            for (int k = 0; k < ROWS + 2; k++) xc[k] = x_at<ST_PLAIN, CG_LOADS>(a, (long long)lr0 - 1 + k);
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                xn[k] = x_at<ST_PLAIN, CG_LOADS>(a, (long long)lr0 + k - n);
+                xs[k] = x_at<ST_PLAIN, CG_LOADS>(a, (long long)lr0 + k + n);
+            }
         }
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
@@ -55,24 +72,24 @@ __global__ void __launch_bounds__(256) stencil5_direct_kernel(const Stencil5Args
             s = fma(cc[3], xc[k + 2], s);
             s = fma(cc[0], xn[k], s);
             s = fma(cc[4], xs[k], s);
-            __stcs(a.y + lr0 + k, s);
+            a.y[lr0 + k] = s;
         }
         return;
     }
     // boundary rows of the grid (and the ragged end of a band): CSR walk, reference order
 #pragma unroll 1
     for (int k = 0; k < ROWS; k++) {
-        const long long lr = lr0 + k;
+        const long long lr = (long long)lr0 + k;
         if (lr >= a.n_local) break;
         const long long r = a.row_offset + lr;
-        const long long gi = r / n, gj = r - gi * n;
-        if (gi >= 1 && gi <= n - 2 && gj >= 1 && gj <= n - 2) {  // interior row next to a boundary one
+        const long long gi = r / a.n, gj = r - gi * a.n;
+        if (gi >= 1 && gi <= a.n - 2 && gj >= 1 && gj <= a.n - 2) {  // interior row next to a boundary one
             const double* v = a.values + (a.base0 + gi * a.row_stride + 5 * gj);
             double s = v[2] * x_at<ST_PLAIN, CG_LOADS>(a, lr);
             s = fma(v[1], x_at<ST_PLAIN, CG_LOADS>(a, lr - 1), s);
             s = fma(v[3], x_at<ST_PLAIN, CG_LOADS>(a, lr + 1), s);
-            s = fma(v[0], x_at<ST_PLAIN, CG_LOADS>(a, lr - n), s);
-            s = fma(v[4], x_at<ST_PLAIN, CG_LOADS>(a, lr + n), s);
+            s = fma(v[0], x_at<ST_PLAIN, CG_LOADS>(a, lr - a.n), s);
+            s = fma(v[4], x_at<ST_PLAIN, CG_LOADS>(a, lr + a.n), s);
             a.y[lr] = s;
         } else {
             (void)boundary_row<ST_PLAIN, CG_LOADS>(a, r, 0.0, 0.0);

@@ -107,8 +107,15 @@ int alloc_block(int dev, void** out) {
 
 }  // namespace
 
-namespace { extern int g_schedule; }
+namespace { extern int g_schedule; int g_precond = 1; }
 extern "C" void b200_cg_set_schedule(int deferred_x) { g_schedule = deferred_x ? 1 : 0; }
+// preconditioner of pcg_solve_device / pcg_solve_mgpu_partitioned: 1 = Jacobi (default), 2 = block-Jacobi with
+// one tridiagonal block per grid row ("line" blocks, clipped to the rank's band)
+extern "C" int b200_pcg_set_preconditioner(int kind) {
+    if (kind != 1 && kind != 2) return 1;
+    g_precond = kind;
+    return 0;
+}
 extern "C" int b200_mgpu_world(void) { return g.inited ? g.world : 1; }
 extern "C" int b200_mgpu_rank(void) { return (g.inited && g.nlocal == 1) ? g.local_rank[0] : 0; }
 extern "C" void b200_mgpu_finalize(void) { mgpu_reset(); }
@@ -195,6 +202,7 @@ struct RankWs {
     uint32_t* tickets = nullptr;
     double* dinv = nullptr;  // Jacobi PCG: 1 / diag(A), allocated on first use
     int* dinv_err = nullptr;
+    double *bj_m = nullptr, *bj_invd = nullptr, *bj_c = nullptr, *z = nullptr;  // block-Jacobi: line factors, z = M^-1 r
     void* scalars = nullptr;
     HostStatus* status = nullptr;  // pinned + mapped
     void* status_dev = nullptr;
@@ -207,7 +215,9 @@ struct RankWs {
         cudaFree(partials); cudaFree(partials2); cudaFree(gsum); cudaFree(tickets); cudaFree(stash); cudaFree(sums);
         cudaFree(scalars);
         cudaFree(dinv); cudaFree(dinv_err);
+        cudaFree(bj_m); cudaFree(bj_invd); cudaFree(bj_c); cudaFree(z);
         dinv = nullptr; dinv_err = nullptr;
+        bj_m = bj_invd = bj_c = z = nullptr;
         x = r = p = p2 = Ap = b = partials = partials2 = gsum = stash = sums = nullptr;
         tickets = nullptr;
         scalars = nullptr;
@@ -395,7 +405,8 @@ namespace {
 
 struct Engine {
     bool fused;           // band kernels available (stencil operators / mgpu); else op->run_device
-    bool pcg = false;     // Jacobi-preconditioned CG (classic launch grouping)
+    bool pcg = false;     // preconditioned CG (classic launch grouping)
+    int precond = 1;      // 1 = Jacobi (z = D^-1 r on the fly), 2 = block-Jacobi, one tridiagonal block per grid row
     SpmvOperator* op;     // generic path
 
     // per-solve parameters shared by the rank threads
@@ -446,24 +457,40 @@ struct Engine {
         memset((void*)w.status, 0, sizeof(HostStatus));
         B200_CUDA(cudaMemcpyAsync(w.b, b_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
         B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
+        const bool bj = pcg && precond == 2;
         if (pcg) {
-            // untimed set-up like the uploads: dinv = 1 / diag(A), rebuilt for every solve (the matrix
-            // behind an operator may have changed while the shape stayed the same)
+            // untimed set-up like the uploads: dinv = 1 / diag(A) -- or the line factors of the block-Jacobi
+            // preconditioner -- rebuilt for every solve (the matrix behind an operator may have changed
+            // while the shape stayed the same)
             int ell_width = 0;
             const DeviceBand* m = fused ? &w.band : operator_matrix(op, &ell_width);
-            if (!m) { fprintf(stderr, "[ERROR] Jacobi PCG needs one of this library's operators (diagonal access)\n"); return 1; }
+            if (!m) { fprintf(stderr, "[ERROR] PCG needs one of this library's operators (matrix access)\n"); return 1; }
             if (m->layout == 1 && ell_width == 0) ell_width = 5;  // stencil ELLPACK band
-            if (!w.dinv) {
-                B200_CUDA(cudaMalloc(&w.dinv, (size_t)w.nl * sizeof(double)));
-                B200_CUDA(cudaMalloc(&w.dinv_err, sizeof(int)));
-            }
+            if (!w.dinv_err) B200_CUDA(cudaMalloc(&w.dinv_err, sizeof(int)));
             B200_CUDA(cudaMemsetAsync(w.dinv_err, 0, sizeof(int), w.st));
-            B200_K(b200_pcg_diag_inv(m->layout == 0 ? m->d_row_ptr : nullptr, m->d_col_idx, m->d_values, w.nl, w.off, ell_width,
-                                     w.dinv, w.dinv_err, w.st));
+            if (bj) {
+                if (ws.grid < 1 || (long long)ws.grid * ws.grid != ws.N) {
+                    fprintf(stderr, "[ERROR] block-Jacobi (line blocks) needs a grid matrix (STENCIL_GRID_SIZE)\n");
+                    return 1;
+                }
+                if (!w.bj_m) {
+                    const size_t vb = (size_t)w.nl * sizeof(double);
+                    B200_CUDA(cudaMalloc(&w.bj_m, vb));
+                    B200_CUDA(cudaMalloc(&w.bj_invd, vb));
+                    B200_CUDA(cudaMalloc(&w.bj_c, vb));
+                    B200_CUDA(cudaMalloc(&w.z, vb));
+                }
+                B200_K(b200_bj_factor(m->layout == 0 ? m->d_row_ptr : nullptr, m->d_col_idx, m->d_values, w.nl, w.off, ws.grid,
+                                      ell_width, w.bj_m, w.bj_invd, w.bj_c, w.dinv_err, w.st));
+            } else {
+                if (!w.dinv) B200_CUDA(cudaMalloc(&w.dinv, (size_t)w.nl * sizeof(double)));
+                B200_K(b200_pcg_diag_inv(m->layout == 0 ? m->d_row_ptr : nullptr, m->d_col_idx, m->d_values, w.nl, w.off, ell_width,
+                                         w.dinv, w.dinv_err, w.st));
+            }
             int bad = 0;
             B200_CUDA(cudaMemcpyAsync(&bad, w.dinv_err, sizeof(int), cudaMemcpyDeviceToHost, w.st));
             B200_CUDA(cudaStreamSynchronize(w.st));
-            if (bad) { fprintf(stderr, "[ERROR] Jacobi PCG: a row has no (or a zero) diagonal entry\n"); return 1; }
+            if (bad) { fprintf(stderr, "[ERROR] PCG: a row has no (or a zero) diagonal entry / a singular line block\n"); return 1; }
         }
         B200_CUDA(cudaStreamSynchronize(w.st));
         if (multi) {
@@ -496,8 +523,9 @@ struct Engine {
         mark(T_INIT_R);
         if (combine(B200_RED_RR0, 0)) return 1;
         if (team.lockstep()) mark(T_RED_RR0);
-        if (pcg) {  // p0 = z0 = D^-1 r0, rho_0 = r0.z0
-            B200_K(b200_pcg_init(w.nl, w.r, w.dinv, w.p, &ctx, w.st));
+        if (pcg) {  // p0 = z0 = M^-1 r0, rho_0 = r0.z0
+            if (bj) B200_K(b200_bj_solve(w.nl, w.off, ws.grid, nullptr, w.bj_m, w.bj_invd, w.bj_c, w.r, w.z, w.st));
+            B200_K(b200_pcg_init(w.nl, w.r, bj ? nullptr : w.dinv, bj ? w.z : nullptr, w.p, &ctx, w.st));
             if (combine(B200_RED_RZ0, 0)) return 1;
         }
         const bool dx = fused && schedule_deferred_x() && !pcg;
@@ -548,7 +576,7 @@ struct Engine {
                 } else {
                     // foreign operator (or unaligned arrays): SpMV through the vtable, then the dot pass
                     if (op->run_device(w.p, w.Ap) != 0) return 1;
-                    B200_K(b200_dot_partials(w.nl, w.Ap, w.p, &ctx, w.st));
+                    B200_K(b200_dot_partials(w.nl, w.Ap, w.p, B200_RED_PAP, &ctx, w.st));
                 }
             }
             mark(T_SPMV, it);
@@ -563,6 +591,8 @@ struct Engine {
                 // K2r: r -= alpha Ap, r.r -> convergence, beta; multi-GPU: the edges of the new r go straight
                 // into the neighbours' landing buffers
                 B200_K(b200_cg_update_r(w.nl, w.Ap, w.r, (dx && multi) ? &push : nullptr, &ctx, w.st));
+            } else if (bj) {  // K2: the r.r tail only tests convergence; z and r.z follow
+                B200_K(b200_pcg_update_xr_stored_z(w.nl, w.p, w.Ap, w.x, w.r, &ctx, w.st));
             } else if (pcg) {  // K2p: + r.z with z = D^-1 r
                 B200_K(b200_pcg_update_xr(w.nl, w.p, w.Ap, w.dinv, w.x, w.r, &ctx, w.st));
             } else {  // K2: x += alpha p, r -= alpha Ap, r.r
@@ -572,8 +602,13 @@ struct Engine {
             nvtxRangePop();
             if (team.lockstep()) {
                 Nvtx range_dot("Dot_Product");
-                if (combine(pcg ? B200_RED_PCG : B200_RED_RR, pcg ? 1 : 0)) return 1;
+                if (combine(bj ? B200_RED_RRC : pcg ? B200_RED_PCG : B200_RED_RR, (pcg && !bj) ? 1 : 0)) return 1;
                 mark(T_RED_RR, it);
+            }
+            if (bj) {  // z = M^-1 r (one Thomas solve per grid row of the band), rho_new = r.z -> beta
+                B200_K(b200_bj_solve(w.nl, w.off, ws.grid, w.scalars, w.bj_m, w.bj_invd, w.bj_c, w.r, w.z, w.st));
+                B200_K(b200_dot_partials(w.nl, w.r, w.z, B200_RED_RZ, &ctx, w.st));
+                if (combine(B200_RED_RZ, 0)) return 1;
             }
             if (dx && multi) {
                 // halo copies of the next direction: p_halo = r_halo + beta p_halo_old (the r edges were pushed
@@ -588,7 +623,8 @@ struct Engine {
             }
             if (!dx) {
                 Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
-                if (pcg) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, multi ? &push : nullptr, w.st));  // K3p
+                if (bj) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.z, nullptr, w.p, multi ? &push : nullptr, w.st));      // K3: p = z + beta p
+                else if (pcg) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, multi ? &push : nullptr, w.st));  // K3p
                 else if (px) B200_K(b200_cg_update_px(w.nl, w.scalars, w.r, w.p, w.x, w.st));                      // K3x
                 else if (!multi) B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));                        // K3
                 else B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, &push, w.st));  // K3 + halo push
@@ -835,6 +871,7 @@ int solve_single(SpmvOperator* op, MatrixData* mat, const double* b, double* x, 
     if (prepare_workspace(mat, op, fused_from_op, &eng)) return 1;
     eng.fused = fused_from_op;
     eng.pcg = pcg;
+    eng.precond = g_precond;
     SolveOut o;
     int rc = eng.solve(b, x, cfg.max_iters, cfg.tolerance, cfg.verbose, cfg.enable_detailed_timers, tag, &o);
     if (rc) return rc;
@@ -920,6 +957,7 @@ int solve_mgpu(MatrixData* mat, const double* b, double* x, CGConfigMultiGPU con
     eng.op = nullptr;
     eng.fused = true;
     eng.pcg = pcg;
+    eng.precond = g_precond;
     if (prepare_workspace(mat, nullptr, false, &eng)) return 1;
     SolveOut o;
     int rc = eng.solve(b, x, config.max_iters, config.tolerance, config.verbose, config.enable_detailed_timers,

@@ -93,6 +93,7 @@ MatrixData b200_synthetic_stencil(int grid_size);
 int b200_set_tuning(int variant, int rows_per_item);
 void b200_get_tuning(int* variant, int* rows_per_item);
 int b200_last_phase_times(double* ms9, int* count9);
+int b200_pcg_set_preconditioner(int kind);
 int b200_last_tail_times(double* ms8, int* count8);
 int b200_last_gap_times(double* ms8);
 int b200_mgpu_halo_probe(int reps, double* us_per_push, long long* bytes_per_direction);

@@ -492,6 +492,113 @@ int orc_pcg_device(const orc_csr* A, int grid, int op, const double* b, double* 
 }
 
 
+/* Block-Jacobi-preconditioned CG with LINE blocks.  NOT in the reference (parity unpinned, like
+ * orc_pcg_device whose conventions it shares): M = the tridiagonal part (W, C, E) of A inside every grid
+ * row, clipped to the row bands of a P-rank partition (orc_partition), so that the multi-GPU solver and
+ * this restatement use the same blocks.  z = M^-1 r: Thomas algorithm per block, operations contracted
+ * the way nvcc contracts the device code (m_j = a_j / d'_{j-1}; d'_j = fma(-m_j, c_{j-1}, d_j);
+ * y_j = fma(-m_j, y_{j-1}, r_j); z_j = fma(-c_j, z_{j+1}, y_j) * (1 / d'_j)).
+ * Loop: alpha = rho / p.Ap; x += alpha p; r -= alpha Ap; stop on ||r|| / ||r0|| < tol; z = M^-1 r;
+ * beta = r.z / rho; p = z + beta p. */
+static double csr_coeff(const orc_csr* A, int row, int col) {
+    double v = 0.0;
+    for (int k = A->row_ptr[row]; k < A->row_ptr[row + 1]; k++)
+        if (A->col_indices[k] == col) v = A->values[k];
+    return v;
+}
+
+int orc_pcg_block_device(const orc_csr* A, int grid, int op, int P, const double* b, double* x, int max_iters,
+                         double tol, orc_cg_result* res) {
+    int n = A->nb_rows;
+    if (grid < 1 || (long long)grid * grid != n || P < 1) return 3;
+    double* r = (double*)malloc((size_t)n * sizeof(double));
+    double* z = (double*)malloc((size_t)n * sizeof(double));
+    double* p = (double*)malloc((size_t)n * sizeof(double));
+    double* Ap = (double*)malloc((size_t)n * sizeof(double));
+    double* m = (double*)malloc((size_t)n * sizeof(double));
+    double* invd = (double*)malloc((size_t)n * sizeof(double));
+    double* c = (double*)malloc((size_t)n * sizeof(double));
+    int* blk_lo = (int*)malloc(((size_t)grid + 2 * (size_t)P + 2) * sizeof(int));
+    if (!r || !z || !p || !Ap || !m || !invd || !c || !blk_lo) return 1;
+    /* blocks: (grid row) x (band) intersections, in row order */
+    int nblk = 0;
+    for (int g = 0; g < P; g++) {
+        int64_t nl, off;
+        orc_partition(n, P, g, &nl, &off);
+        int64_t s = off;
+        while (s < off + nl) {
+            int64_t e = (s / grid + 1) * grid;
+            if (e > off + nl) e = off + nl;
+            blk_lo[nblk++] = (int)s;
+            s = e;
+        }
+    }
+    blk_lo[nblk] = n;
+    int bad = 0;
+#pragma omp parallel for schedule(static)
+    for (int bi = 0; bi < nblk; bi++) {
+        double dprev = 1.0, cprev = 0.0;
+        for (int i = blk_lo[bi]; i < blk_lo[bi + 1]; i++) {
+            double d = csr_coeff(A, i, i);
+            double a = i > blk_lo[bi] ? csr_coeff(A, i, i - 1) : 0.0;
+            double cc = i + 1 < blk_lo[bi + 1] ? csr_coeff(A, i, i + 1) : 0.0;
+            double mj = i > blk_lo[bi] ? a / dprev : 0.0;
+            double dj = fma(-mj, cprev, d);
+            if (dj == 0.0 || d == 0.0) bad = 1;
+            m[i] = mj; invd[i] = 1.0 / dj; c[i] = cc;
+            dprev = dj; cprev = cc;
+        }
+    }
+    if (bad) { free(r); free(z); free(p); free(Ap); free(m); free(invd); free(c); free(blk_lo); return 2; }
+#define ORC_BJ_SOLVE()                                                           \
+    _Pragma("omp parallel for schedule(static)")                                 \
+    for (int bi = 0; bi < nblk; bi++) {                                          \
+        double y = 0.0;                                                          \
+        for (int i = blk_lo[bi]; i < blk_lo[bi + 1]; i++) { y = fma(-m[i], y, r[i]); z[i] = y; } \
+        double zn = 0.0;                                                         \
+        for (int i = blk_lo[bi + 1] - 1; i >= blk_lo[bi]; i--) { zn = fma(-c[i], zn, z[i]) * invd[i]; z[i] = zn; } \
+    }
+    apply_op(A, grid, op, x, Ap);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) r[i] = fma(1.0, b[i], -1.0 * Ap[i]);
+    ORC_BJ_SOLVE();
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) p[i] = z[i];
+    double rr0 = orc_dot_blocktree(n, r, r);
+    double rho = orc_dot_blocktree(n, r, z);
+    double b_norm = sqrt(rr0);
+    double final_res = b_norm;
+    int iter;
+    for (iter = 0; iter < max_iters; iter++) {
+        apply_op(A, grid, op, p, Ap);
+        double pAp = orc_dot_blocktree(n, Ap, p);
+        double alpha = rho / pAp;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) { x[i] = fma(alpha, p[i], x[i]); r[i] = fma(-alpha, Ap[i], r[i]); }
+        double rr_new = orc_dot_blocktree(n, r, r);
+        double resn = sqrt(rr_new);
+        final_res = resn;
+        if (resn / b_norm < tol) { iter++; break; }
+        ORC_BJ_SOLVE();
+        double rho_new = orc_dot_blocktree(n, r, z);
+        double beta = rho_new / rho;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) p[i] = fma(beta, p[i], z[i]);
+        rho = rho_new;
+    }
+#undef ORC_BJ_SOLVE
+    res->iterations = iter;
+    res->residual_norm = final_res;
+    res->b_norm = b_norm;
+    res->converged = (final_res / b_norm < tol) ? 1 : 0;
+    double s = 0.0, s2 = 0.0;
+    for (int i = 0; i < n; i++) { s += x[i]; s2 += x[i] * x[i]; }
+    res->solution_sum = s;
+    res->solution_norm = sqrt(s2);
+    free(r); free(z); free(p); free(Ap); free(m); free(invd); free(c); free(blk_lo);
+    return 0;
+}
+
 /* src/solvers/cg_solver_mgpu_partitioned.cu:262-268: n_local = N / P (matrix rows),
  * row_offset = g * n_local, the last rank takes N - row_offset. */
 void orc_partition(int64_t N, int P, int g, int64_t* n_local, int64_t* row_offset) {

@@ -104,6 +104,9 @@ int orc_cg_device(const orc_csr* A, int grid, int op, const double* b, double* x
 /* Jacobi-preconditioned CG (not in the reference: parity unpinned), same conventions as orc_cg_device */
 int orc_pcg_device(const orc_csr* A, int grid, int op, const double* b, double* x, int max_iters,
                    double tol, orc_cg_result* res);
+/* block-Jacobi (one tridiagonal block per grid row, clipped to the bands of a P-rank partition) */
+int orc_pcg_block_device(const orc_csr* A, int grid, int op, int P, const double* b, double* x, int max_iters,
+                         double tol, orc_cg_result* res);
 int orc_cg_mgpu(const orc_csr* A, int grid, int P, const double* b, double* x, int max_iters,
                 double tol, orc_cg_result* res);
 

@@ -269,6 +269,21 @@ def pcg_device(rp, ci, va, grid, op, b, x0, max_iters=1000, tol=1e-6):
     return x, {k: getattr(res, k) for k, _ in CGResult._fields_}
 
 
+def pcg_block_device(rp, ci, va, grid, op, P, b, x0, max_iters=1000, tol=1e-6):
+    """block-Jacobi PCG, line blocks clipped to a P-band partition (oracle-only convention).  -> (x, result dict)"""
+    rows = len(rp) - 1
+    c = _csr_struct(rp, ci, va, rows, rows)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    res = CGResult()
+    f = lib().orc_pcg_block_device
+    f.argtypes = [C.POINTER(CSR), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(CGResult)]
+    rc = f(C.byref(c), grid, op, P, _p(b), _p(x), max_iters, tol, C.byref(res))
+    if rc:
+        raise RuntimeError("orc_pcg_block_device rc=%d" % rc)
+    return x, {k: getattr(res, k) for k, _ in CGResult._fields_}
+
+
 def cg_mgpu(rp, ci, va, grid, P, b, x0, max_iters=1000, tol=1e-6):
     rows = len(rp) - 1
     c = _csr_struct(rp, ci, va, rows, rows)

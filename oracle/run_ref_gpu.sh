@@ -54,6 +54,31 @@ for n, center in sizes:
                               "solution_norm": j["validation"]["solution_norm"], "median_ms": j["timing"]["median_ms"]}
     for op, c in case["cg"].items():
         c["ms_per_iteration"] = c["median_ms"] / max(c["iterations"], 1)
+    if os.environ.get("REF_GPU_SAME_BOX_OURS") == "1":
+        # this repo's CLIs on the SAME box and the SAME .mtx file, same protocol (5 warm-ups + 10 runs, median):
+        # the only apples-to-apples comparison with the reference's kernels (GPUs of the pool differ by a few %)
+        ours = {"spmv": {}, "cg": {}}
+        bindir = "cuda-spmv-benchmark_b200/bin"
+        r = subprocess.run([bindir + "/spmv_bench", mtx, "--mode=stencil5-csr,cusparse-csr", "--device-ingest",
+                            "--json=%s/ours_spmv_%d.json" % (out, n)], capture_output=True, text=True)
+        open(os.path.join(out, "ours_spmv_%d.log" % n), "w").write(r.stdout + r.stderr)
+        for op in ("stencil5-csr", "cusparse-csr"):
+            p = "%s/ours_spmv_%d_%s.json" % (out, n, op)
+            if os.path.exists(p):
+                j = json.load(open(p))
+                ours["spmv"][op] = {"sum_y": j["benchmark"]["validation"]["sum_y"],
+                                    "execution_time_ms": j["benchmark"]["performance"]["execution_time_ms"]}
+        for op in ("stencil5-csr", "cusparse-csr"):
+            r = subprocess.run([bindir + "/cg_solver", mtx, "--mode=%s" % op, "--device-ingest", "--json=%s/ours_cg_%d" % (out, n)],
+                               capture_output=True, text=True)
+            open(os.path.join(out, "ours_cg_%d_%s.log" % (n, op)), "w").write(r.stdout + r.stderr)
+            p = "%s/ours_cg_%d_%s.json" % (out, n, op)
+            if os.path.exists(p):
+                j = json.load(open(p))
+                ours["cg"][op] = {"iterations": j["convergence"]["iterations"], "median_ms": j["timing"]["median_ms"],
+                                  "ms_per_iteration": j["timing"]["median_ms"] / max(j["convergence"]["iterations"], 1),
+                                  "solution_sum": j["validation"]["solution_sum"]}
+        case["this_repo_same_box"] = ours
     case["wall_s"] = round(time.time() - t_case, 1)
     cases.append(case)
     os.remove(mtx)

@@ -349,6 +349,59 @@ def test_pcg_mgpu_virtual_ranks_matches_oracle(B, orc, torch_cuda, n, P):
             L.b200_mgpu_finalize()
 
 
+@pytest.mark.parametrize("opname", [b"stencil5-csr", b"cusparse-csr", b"ellpack", b"stencil5-ellpack"])
+@pytest.mark.parametrize("n", [40, 257])
+def test_pcg_block_jacobi_matches_oracle(B, orc, torch_cuda, opname, n):
+    """block-Jacobi with line blocks (one tridiagonal block per grid row; SURVEY 8f-3, parity = the oracle's
+    restatement): same iteration count as the oracle, solution within 1e-10, not more iterations than Jacobi"""
+    L = B.load()
+    N = n * n
+    ent = variable_diagonal_stencil(orc, n, n)
+    hm = B.HostMatrix.from_entries(N, N, ent, grid_size=n)
+    orp, oci, ova = orc.build_csr(N, N, ent)
+    rng = np.random.default_rng(2)
+    b, x0 = rng.standard_normal(N), np.zeros(N)
+    xj, sj, op = solve_device(B, opname, hm, b, x0, entry="pcg_solve_device")
+    assert L.b200_pcg_set_preconditioner(2) == 0
+    try:
+        xb, sb, op = solve_device(B, opname, hm, b, x0, entry="pcg_solve_device")
+    finally:
+        L.b200_pcg_set_preconditioner(1)
+    op.contents.free()
+    xo, ro = orc.pcg_block_device(orp, oci, ova, n, 1 if opname.startswith(b"stencil5") else 0, 1, b, x0)
+    assert sb["converged"] == 1 == ro["converged"] and sb["iterations"] == ro["iterations"]
+    assert np.linalg.norm(xb - xo) / np.linalg.norm(xo) < 1e-10
+    assert abs(sb["residual_norm"] - ro["residual_norm"]) <= 1e-9 * ro["b_norm"]
+    assert sb["iterations"] <= sj["iterations"]
+    assert np.linalg.norm(xb - xj) / np.linalg.norm(xj) < 1e-5
+
+
+@pytest.mark.parametrize("n,P", [(40, 2), (130, 3), (81, 4)])
+def test_pcg_block_jacobi_mgpu_virtual_ranks(B, orc, torch_cuda, n, P):
+    """the same over P row bands: blocks are clipped at the band boundaries (81 x 81 over 4 ranks cuts grid rows
+    in the middle), the oracle uses the same blocks; edges of the new direction travel like in Jacobi PCG"""
+    L = B.load()
+    N = n * n
+    devs = (C.c_int * P)(*([0] * P))
+    ent = variable_diagonal_stencil(orc, n, n + P)
+    hm = B.HostMatrix.from_entries(N, N, ent, grid_size=n)
+    orp, oci, ova = orc.build_csr(N, N, ent)
+    b = np.random.default_rng(P).standard_normal(N)
+    xo, ro = orc.pcg_block_device(orp, oci, ova, n, 1, P, b, np.zeros(N))
+    assert L.b200_pcg_set_preconditioner(2) == 0
+    assert L.b200_mgpu_init_single_process(P, devs, n) == 0
+    try:
+        x = np.zeros(N)
+        st = B.CGStatsMultiGPU()
+        rc = L.pcg_solve_mgpu_partitioned(None, hm.ptr(), b.ctypes.data, x.ctypes.data, B.cg_config(), C.byref(st))
+        assert rc == 0
+        assert st.converged == 1 and st.iterations == ro["iterations"]
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    finally:
+        L.b200_mgpu_finalize()
+        L.b200_pcg_set_preconditioner(1)
+
+
 def test_pcg_constant_diagonal_equals_cg_iterations(B, orc, torch_cuda):
     """on the 5 / -1 stencil D = 5 I: PCG is CG in exact arithmetic -- same iteration count"""
     n = 300
