@@ -458,35 +458,54 @@ def run_b200(args):
     # direction-update SpMV (values + r + p_old + x in, p_new + x + Ap out = 8 nnz + 48 N bytes);
     # B200_CG_SCHEDULE=classic runs the plain one every iteration.
     deferred_x = os.environ.get("B200_CG_SCHEDULE", "") != "classic"
+    sweep_family = L.b200_cg_get_kernel() == 1
+    xdepth = L.b200_cg_set_xdepth(0) if (deferred_x and sweep_family) else 1  # 0 = query; ring kernels: depth 1
+    kname = "stencil5_sweep_kernel" if sweep_family else "stencil5_kernel"
     dot_bytes = 8.0 * nnz_local + 16.0 * rows_local
-    fused_bytes = 8.0 * nnz_local + 48.0 * rows_local
+
+    def fused_bytes_nx(nx):
+        """values + r + p_old in, p_new + Ap out; a launch that retires nx pending x updates also reads and
+        writes x once and reads the nx - 1 older directions"""
+        return 8.0 * nnz_local + 32.0 * rows_local + ((16.0 + 8.0 * (nx - 1)) * rows_local if nx > 0 else 0.0)
+
+    # launches of one solve: iteration 0 is the plain SpMV + p.Ap, iteration it >= 1 the fused one, which
+    # retires the last `xdepth` x updates when it % xdepth == 0 (DESIGN.md section 3.3)
+    nx_of = [None] + [(xdepth if it % xdepth == 0 else 0) for it in range(1, iters or 1)]
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    measured = {}
+    if os.path.exists(tp) and world == 1:  # the ncu captures are of one-GPU launches: not a measurement of a band
+        try:
+            measured = json.load(open(tp))
+        except Exception:
+            measured = {}
     if deferred_x and iters and iters > 1:
-        k1_bytes = (dot_bytes + (iters - 1) * fused_bytes) / iters  # mean over the launches of a solve
-        k1_name = "stencil5_kernel<ST_FUSED> (p = r + beta p, x += alpha p, SpMV, p.Ap; 1 of %d launches is the plain ST_DOT)" % iters
-        traffic_key = "stencil5_fused_dram_bytes_per_launch_%d" % n
-        traffic_alg = fused_bytes
+        per_launch = [dot_bytes] + [fused_bytes_nx(nx) for nx in nx_of[1:]]
+        k1_bytes = sum(per_launch) / iters  # mean over the launches of a solve
+        mix = {nx: nx_of[1:].count(nx) for nx in sorted(set(nx_of[1:]))}
+        k1_name = ("%s<ST_FUSED*>: p = r + beta p, SpMV, p.Ap, and x += alpha p for the last %d iterations in every "
+                   "%s launch; per solve of %d iterations: 1 x ST_DOT, %s"
+                   % (kname, xdepth, "launch" if xdepth == 1 else "%d-th" % xdepth, iters,
+                      ", ".join("%d x %s" % (c, "ST_FUSED_X%d" % nx if nx != 1 else "ST_FUSED") for nx, c in mix.items())))
+        fam = "sweep" if sweep_family else "ring"
+        keys = ["stencil5_%s_dot_dram_bytes_per_launch_%d" % (fam, n)] + \
+               ["stencil5_%s_fused_x%d_dram_bytes_per_launch_%d" % (fam, nx, n) for nx in nx_of[1:]]
+        traffic = (sum(measured[k] for k in keys) / iters) if all(k in measured for k in keys) else None
+        traffic_alg = k1_bytes
+        pending = iters - xdepth * ((iters - 1) // xdepth)
+        iter_bytes = (96.0 + 8.0 + 8.0 / xdepth) * rows_local  # K1F 72 + K2r 24 + x (16 + 8 (d - 1)) / d
+        solve_bytes = 72.0 * rows_local + sum(per_launch) + 24.0 * iters * rows_local + (16.0 + 8.0 * pending) * rows_local
+        schedule = ("deferred-x, depth %d (2 launches, %.1f B/row per iteration; %s kernels)" % (xdepth, iter_bytes / rows_local, fam))
     else:
         k1_bytes = dot_bytes
-        k1_name = "stencil5_kernel<ST_DOT> (SpMV + p.Ap)"
-        traffic_key = "stencil5_dot_dram_bytes_per_launch_%d" % n
+        k1_name = "%s<ST_DOT> (SpMV + p.Ap)" % kname
+        k = "stencil5_%s_dot_dram_bytes_per_launch_%d" % ("sweep" if sweep_family else "ring", n)
+        traffic = measured.get(k)
         traffic_alg = dot_bytes
-    k1_avg_ms = k1_ms / max(k1_cnt, 1)
-    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_cnt else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(traffic_key)
-            if world > 1:  # the ncu capture is of the one-GPU launch: not a measurement of a band
-                traffic = None
-        except Exception:
-            traffic = None
-    if deferred_x:
-        iter_bytes = 112.0 * rows_local          # K1F 88 + K2r 24 (interior rows)
-        solve_bytes = (72.0 + 56.0 + 88.0 * (iters - 1) + 24.0 * iters + 24.0) * rows_local
-    else:
         iter_bytes = 128.0 * rows_local          # K1 56 + K2 48 + K3 24
         solve_bytes = (72.0 + 128.0 * iters) * rows_local
+        schedule = "classic (3 launches, 128 B/row per iteration)"
+    k1_avg_ms = k1_ms / max(k1_cnt, 1)
+    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9 if k1_cnt else None
     line = {
         "metric": METRIC if not args.weak else "cg_solve_ms_weak_20k_x_20k_rows_per_gpu_stencil5_fp64",
         "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -514,8 +533,7 @@ def run_b200(args):
         "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV launch inside CG (see roofline.kernel)"},
         "cg": {"iterations": iters, "residual_norm": stats.residual_norm, "solution_sum": stats.solution_sum,
                "solution_norm": stats.solution_norm,
-               "schedule": "deferred-x (2 launches, 112 B/row per iteration)" if deferred_x
-               else "classic (3 launches, 128 B/row per iteration)",
+               "schedule": schedule,
                "topology": ("one process, %d GPUs, one enqueue thread per GPU" % world) if single
                else ("one process per GPU (torchrun), peer memory via CUDA IPC" if world > 1 else "one GPU"),
                "iter_bytes_model": iter_bytes, "solve_bytes_model": solve_bytes,

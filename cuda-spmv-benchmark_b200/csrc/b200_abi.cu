@@ -19,6 +19,9 @@
 #ifndef B200_PLAIN_VARIANT_DEFAULT
 #define B200_PLAIN_VARIANT_DEFAULT 20
 #endif
+#ifndef B200_CG_KERNEL_DEFAULT
+#define B200_CG_KERNEL_DEFAULT 1
+#endif
 #ifndef B200_PDL_DEFAULT
 #define B200_PDL_DEFAULT 3
 #endif
@@ -122,6 +125,7 @@ int current_device() {
 struct Geometry {
     Stencil5Args a;
     TailArgs tail;  // what follows the launch: fixed-order sum of the partials + exchange + recurrence (cg_reduce_kernel)
+    bool sweep = false;  // fused CG passes in sequential-sweep form (csrc/stencil5_direct.cuh) instead of the ring
     int grid;
     int threads;
     size_t smem;
@@ -222,13 +226,54 @@ int launch_variant(int v, const Geometry& g, cudaStream_t s) {
     }
 }
 
+// kernel family of the fused CG passes: 0 = bulk-copy ring (csrc/stencil5.cuh), 1 = sequential sweep
+// (csrc/stencil5_direct.cuh, the default: equal or faster in every fused mode, and it has the registers for
+// the deeper x retirement modes).  B200_CG_KERNEL=ring|sweep, b200_cg_set_kernel().  All three passes
+// (residual init, SpMV + p.Ap, fused direction update) switch together: the CG schedules stay bit-identical.
+std::atomic<int> g_cg_kernel{-1};
+int cg_kernel_choice() {
+    int v = g_cg_kernel.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("B200_CG_KERNEL");
+        v = e ? (strcmp(e, "ring") == 0 ? 0 : 1) : B200_CG_KERNEL_DEFAULT;
+        g_cg_kernel.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+int sweep_grid(long long n_local) {
+    const long long rows_per_cta = 256LL * SWEEP_TILES;
+    return (int)((n_local + rows_per_cta - 1) / rows_per_cta);
+}
+// called by the CG launchers right after build_geometry: the partial count follows the kernel family
+void choose_cg_kernel(Geometry& g, bool force_sweep = false) {
+    if ((force_sweep || cg_kernel_choice() == 1) && g.a.n_local > 0) {
+        g.sweep = true;
+        g.grid = sweep_grid(g.a.n_local);
+    }
+}
+
+template <int MODE>
+int launch_sweep(const b200_band* b, Geometry& g, cudaStream_t s) {
+    const bool cg = (b->d_halo_prev != nullptr || b->d_halo_next != nullptr);
+    if (cg) launch_pdl<2>(stencil5_sweep_kernel<MODE, true>, g.grid, 256, 0, s, g.a);
+    else launch_pdl<2>(stencil5_sweep_kernel<MODE, false>, g.grid, 256, 0, s, g.a);
+    return check_launch("stencil5_sweep_kernel");
+}
+
 template <int MODE>
 int launch_stencil(const b200_band* b, Geometry& g, cudaStream_t s) {
     if (g.grid == 0) return B200_OK;
+    if (MODE != ST_PLAIN && g.sweep) return launch_sweep<MODE>(b, g, s);
+    // the ring kernel sits at its register limit with one x update per launch (128: 4 CTAs per SM); with a
+    // second direction stream it spills (measured 7.24 against 5.80 ms at 20k x 20k), so the deeper x
+    // retirement modes exist in sweep form only
+    if constexpr (st_fused(MODE) && st_nx(MODE) != 1) return fail(B200_EINVAL, "stencil5: this mode runs on the sweep kernel only");
+    else {
     const int v = (b->variant >= 0 && b->variant < kNumVariants && kVariants[b->variant].info) ? b->variant : 0;
     // peer-written halos must be read through L2 (ld.global.cg); single-GPU uses the read-only path
     const bool cg = (b->d_halo_prev != nullptr || b->d_halo_next != nullptr);
     return cg ? launch_variant<MODE, true>(v, g, s) : launch_variant<MODE, false>(v, g, s);
+    }
 }
 
 }  // namespace
@@ -244,8 +289,11 @@ extern "C" int b200_stencil5_num_partials(const b200_band* band) {
     Geometry g;
     static const double dummy = 0;
     if (build_geometry(band, &dummy, &g) != B200_OK) return -1;
-    return g.grid;
+    const int sw = sweep_grid(band->n_local);  // either kernel family may run: room for the larger grid
+    return g.grid > sw ? g.grid : sw;
 }
+extern "C" void b200_cg_set_kernel(int sweep) { g_cg_kernel.store(sweep ? 1 : 0, std::memory_order_relaxed); }
+extern "C" int b200_cg_get_kernel(void) { return cg_kernel_choice(); }
 
 namespace {
 // plain product, sequential-sweep form (csrc/stencil5_direct.cuh): variants 20 / 21 / 22 = 1 / 2 / 4 rows per thread
@@ -690,6 +738,7 @@ extern "C" int b200_cg_residual_init(const b200_band* band, const double* d_x, c
     int rc = build_geometry(band, d_x, &g);
     if (rc) return rc;
     if (!d_b || !d_r || !d_p) return fail(B200_EINVAL, "cg_residual_init: NULL argument");
+    choose_cg_kernel(g);
     if ((rc = make_tail(ctx, RED_RR0, 0, g.grid, &g.tail, "cg_residual_init"))) return rc;
     g.a.y = d_r; g.a.y2 = d_p; g.a.b = d_b; g.a.partials = ctx->d_partials;
     g.a.error_word = &static_cast<CGScalars*>(ctx->d_scalars)->error;
@@ -702,6 +751,7 @@ extern "C" int b200_cg_spmv_dot(const b200_band* band, const double* d_p, double
     int rc = build_geometry(band, d_p, &g);
     if (rc) return rc;
     if (!d_Ap) return fail(B200_EINVAL, "cg_spmv_dot: NULL argument");
+    choose_cg_kernel(g);
     if ((rc = make_tail(ctx, RED_PAP, 0, g.grid, &g.tail, "cg_spmv_dot"))) return rc;
     g.a.y = d_Ap; g.a.partials = ctx->d_partials;
     CGScalars* sc = static_cast<CGScalars*>(ctx->d_scalars);
@@ -761,21 +811,41 @@ extern "C" int b200_cg_update_p_push(long long n, const void* d_scalars, const d
     return check_launch("cg_update_p_push_kernel");
 }
 
-extern "C" int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
-                                  double* d_x, double* d_Ap, const b200_reduce_ctx* ctx, b200_stream stream) {
+extern "C" int b200_cg_spmv_fused_nx(const b200_band* band, const double* d_p_old, const double* const* d_p_older, int nx,
+                                     const double* d_r, double* d_p_new, double* d_x, double* d_Ap,
+                                     const b200_reduce_ctx* ctx, b200_stream stream) {
     Geometry g;
     int rc = build_geometry(band, d_p_old, &g);
     if (rc) return rc;
-    if (!d_r || !d_p_new || !d_x || !d_Ap || !ctx || !ctx->d_scalars) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
+    if (!d_r || !d_p_new || !d_Ap || !ctx || !ctx->d_scalars) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
+    if (nx < 0 || nx > ST_MAX_NX || (nx > 0 && !d_x) || (nx > 1 && !d_p_older)) return fail(B200_EINVAL, "cg_spmv_fused: bad x retirement arguments");
     if (d_p_new == d_p_old) return fail(B200_EINVAL, "cg_spmv_fused: p_new must not alias p_old");
+    for (int k = 0; k + 1 < nx; k++)
+        if (!d_p_older[k] || d_p_older[k] == d_p_new) return fail(B200_EINVAL, "cg_spmv_fused: an older direction is NULL or aliases p_new");
+    choose_cg_kernel(g, nx != 1);  // the ring kernel has no registers for an extra direction stream
     if ((rc = make_tail(ctx, RED_PAP, 0, g.grid, &g.tail, "cg_spmv_fused"))) return rc;
     const CGScalars* sc = static_cast<const CGScalars*>(ctx->d_scalars);
     g.a.y = d_Ap; g.a.y2 = d_p_new; g.a.r = d_r; g.a.xs = d_x; g.a.partials = ctx->d_partials;
     g.a.ab = &sc->alpha;
     static_assert(offsetof(CGScalars, beta) == offsetof(CGScalars, alpha) + sizeof(double), "alpha, beta adjacent");
+    for (int k = 0; k + 1 < nx; k++) g.a.xp[k] = d_p_older[k];
+    g.a.alpha_hist = sc->alpha_hist;
+    g.a.iter_ptr = &sc->iterations;
     g.a.converged = &sc->converged;
     g.a.error_word = &const_cast<CGScalars*>(sc)->error;
-    return launch_stencil_cg<ST_FUSED>(band, g, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (nx) {
+        case 0: return launch_stencil_cg<ST_FUSED_X0>(band, g, s);
+        case 1: return launch_stencil_cg<ST_FUSED>(band, g, s);
+        case 2: return launch_stencil_cg<ST_FUSED_X2>(band, g, s);
+        case 3: return launch_stencil_cg<ST_FUSED_X3>(band, g, s);
+        default: return launch_stencil_cg<ST_FUSED_X4>(band, g, s);
+    }
+}
+extern "C" int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
+                                  double* d_x, double* d_Ap, const b200_reduce_ctx* ctx, b200_stream stream) {
+    if (!d_x) return fail(B200_EINVAL, "cg_spmv_fused: NULL argument");
+    return b200_cg_spmv_fused_nx(band, d_p_old, nullptr, 1, d_r, d_p_new, d_x, d_Ap, ctx, stream);
 }
 
 extern "C" int b200_cg_update_r(long long n, const double* d_Ap, double* d_r, const b200_halo_push_args* push,
@@ -827,13 +897,27 @@ extern "C" int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, 
     return check_launch("cg_halo_dir_kernel");
 }
 
+extern "C" int b200_cg_finish_x_depth(long long n, const void* d_scalars, const double* const* d_pbuf, int nbuf, int depth,
+                                      int only_if_converged, double* d_x, b200_stream stream) {
+    if (!d_scalars || !d_pbuf || !d_x) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
+    if (depth < 1 || depth > ST_MAX_NX || nbuf < 1 || nbuf > 5 || (nbuf < depth + 1 && !(depth == 1 && nbuf == 1)))
+        return fail(B200_EINVAL, "cg_finish_x: depth d needs d + 1 direction buffers");
+    FinishXArgs a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < nbuf; k++) {
+        if (!d_pbuf[k]) return fail(B200_EINVAL, "cg_finish_x: NULL direction buffer");
+        a.pbuf[k] = d_pbuf[k];
+    }
+    a.nbuf = nbuf; a.depth = depth; a.only_if_converged = only_if_converged;
+    const int grid = blas1_grid(n, 1);
+    launch_pdl(cg_finish_x_kernel, grid, 256, 0, (cudaStream_t)stream, n, static_cast<const CGScalars*>(d_scalars), a, d_x);
+    return check_launch("cg_finish_x_kernel");
+}
 extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, const double* d_p1,
                                 double* d_x, int only_if_converged, b200_stream stream) {
-    if (!d_scalars || !d_p0 || !d_p1 || !d_x) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
-    const int grid = blas1_grid(n, 1);
-    launch_pdl(cg_finish_x_kernel, grid, 256, 0, (cudaStream_t)stream, n, static_cast<const CGScalars*>(d_scalars), d_p0, d_p1, d_x,
-               only_if_converged);
-    return check_launch("cg_finish_x_kernel");
+    if (!d_p0 || !d_p1) return fail(B200_EINVAL, "cg_finish_x: NULL argument");
+    const double* bufs[2] = {d_p0, d_p1};
+    return b200_cg_finish_x_depth(n, d_scalars, bufs, d_p0 == d_p1 ? 1 : 2, 1, only_if_converged, d_x, stream);
 }
 
 extern "C" int b200_cg_update_px(long long n, const void* d_scalars, const double* d_r, double* d_p, double* d_x,

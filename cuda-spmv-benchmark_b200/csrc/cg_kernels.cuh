@@ -39,6 +39,9 @@ struct CGScalars {
     // kernel(s) of this reduction): per-phase times that cost no events and no synchronisation
     unsigned long long gap_ns[8];
     unsigned long long last_tail_end;
+    // alpha of iteration j at [j & 7]: the STENCIL5 kernel retires several pending x updates at once
+    // (ST_FUSED_X<m>, stencil5.cuh) and cg_finish_x_kernel the ones left at the end
+    double alpha_hist[8];
 };
 
 // host-visible mirror (pinned, mapped), written by the reduction tail after every r.r
@@ -130,7 +133,11 @@ struct TailArgs {
 };
 
 // programmatic dependent launch: a kernel launched with the stream-serialisation attribute may be
-// scheduled while its predecessor drains; everything it reads must come after griddep_wait()
+// scheduled while its predecessor drains; everything it reads must come after griddep_wait().
+// NOTE: the scalar block is therefore never passed as `const ... __restrict__`: that qualifier turns its
+// reads into invariant loads (LDG.CONSTANT), which the compiler is free to schedule ABOVE the wait -- it did,
+// in cg_finish_x_kernel: the iteration count of the previous kernel's tail was read before that tail had run
+// (tests/test_sass_pdl.py scans the SASS of every kernel for global loads in front of the wait).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -287,6 +294,7 @@ __device__ __forceinline__ void cg_tail(const TailArgs& a, double total, double 
     } else if (a.which == RED_PAP) {
         sc->pAp = total;
         sc->alpha = sc->rr_old / total;  // PCG keeps rho = r.z in rr_old
+        sc->alpha_hist[sc->iterations & 7] = sc->alpha;
     } else if (a.which == RED_RZ0) {
         sc->rr_old = total;  // rho_0 = r0.z0 (b_norm was set by RED_RR0)
     } else if (a.which == RED_RZ) {
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(32) cg_reduce_kernel(const ReduceArgs a) {
 // reference: axpy_kernel_device + axpy_sub_kernel_device + dot_kernel (cg_solver.cu:59-78,110-132)
 // contracted the same way (fma(alpha,p,x), fma(-alpha,Ap,r)).
 template <int VEC>
-__global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CGScalars* sc,
                                                            const double* __restrict__ p,
                                                            const double* __restrict__ Ap, double* __restrict__ x,
                                                            double* __restrict__ r, const TailArgs tail) {
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(256) cg_update_xr_kernel(long long n, const CG
 // produce the first / last `halo` elements of r store them straight into the neighbours' landing
 // buffers over NVLink; the last CTA publishes the arrival epoch (as cg_update_p_push_kernel does for p).
 template <int VEC, bool PUSH>
-__global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) cg_update_r_kernel(long long n, const CGScalars* sc,
                                                           const double* __restrict__ Ap, double* __restrict__ r,
                                                           const HaloPushArgs h, const TailArgs tail) {
     __shared__ double scratch[8];
@@ -564,27 +572,46 @@ __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
     }
 }
 
-// After the last iteration of the deferred-x schedule x still lacks alpha_last * p_last.
-// p_last lives in p0 or p1 depending on the parity of the completed iterations (known on the device).
-// only_if_converged: the K3x schedule (below) retires x inside the p update of the same iteration, so an
-// update is pending only when the convergence test stopped the loop in front of that kernel.
-__global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGScalars* __restrict__ sc,
-                                                          const double* __restrict__ p0,
-                                                          const double* __restrict__ p1, double* __restrict__ x,
-                                                          int only_if_converged) {
+// After the last iteration of the deferred-x schedule x still lacks the updates that no SpMV launch has
+// retired.  Direction j lives in pbuf[j % nbuf] (nbuf = depth + 1); the launches of iterations depth, 2 depth,
+// ... each retired the `depth` updates before them, so with c completed iterations (known on the device)
+// the pending ones are j = depth * floor((c - 1) / depth) .. c - 1, applied oldest first.
+// only_if_converged (depth 1, p0 == p1): the K3x schedule (below) retires x inside the p update of the same
+// iteration, so an update is pending only when the convergence test stopped the loop in front of that kernel.
+struct FinishXArgs {
+    const double* pbuf[5];
+    int nbuf;
+    int depth;
+    int only_if_converged;
+};
+__global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGScalars* sc,
+                                                          const FinishXArgs a, double* __restrict__ x) {
     griddep_wait();
-    const int it = sc->iterations;
-    if (it <= 0) return;
-    if (only_if_converged && !sc->converged) return;
-    const double alpha = sc->alpha;
-    const double* __restrict__ p = ((it - 1) & 1) ? p1 : p0;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
-        x[i] = fma(alpha, p[i], x[i]);
+    const int c = sc->iterations;
+    if (c <= 0) return;
+    if (a.only_if_converged && !sc->converged) return;
+    const int first = a.depth * ((c - 1) / a.depth);
+    const int cnt = c - first;  // 1 .. depth
+    double al[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* p[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; k++)
+        if (k < cnt) {
+            const int j = first + k;
+            al[k] = (j == c - 1) ? sc->alpha : sc->alpha_hist[j & 7];
+            p[k] = a.pbuf[j % a.nbuf];
+        }
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        double xv = x[i];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < cnt) xv = fma(al[k], p[k][i], xv);
+        x[i] = xv;
+    }
 }
 
 // K3: p = r + beta p   (reference update_p_kernel, cg_solver.cu:91-96: fma(beta,p,r))
 template <int VEC>
-__global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGScalars* sc,
                                                           const double* __restrict__ r, double* __restrict__ p) {
     griddep_wait();
     if (sc->converged) return;
@@ -632,7 +659,7 @@ __global__ void __launch_bounds__(256) cg_update_p_kernel(long long n, const CGS
 // bit-identical to the classic schedule.  alpha is still the alpha of this iteration: the next p.Ap tail
 // has not run yet.
 template <int VEC>
-__global__ void __launch_bounds__(256) cg_update_px_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) cg_update_px_kernel(long long n, const CGScalars* sc,
                                                            const double* __restrict__ r, double* __restrict__ p,
                                                            double* __restrict__ x) {
     griddep_wait();
@@ -730,7 +757,7 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(long long n, const double
 }
 
 // K2p: x += alpha p ; r -= alpha Ap ; partials of r.r (convergence) and r.z (rho), z = dinv r
-__global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const CGScalars* sc,
                                                             const double* __restrict__ p,
                                                             const double* __restrict__ Ap,
                                                             const double* __restrict__ dinv, double* __restrict__ x,
@@ -769,7 +796,7 @@ __global__ void __launch_bounds__(256) pcg_update_xr_kernel(long long n, const C
 // K3p: p = z + beta p, z = dinv r.  Multi-GPU (h.my_xchg != NULL): the first / last `halo` elements of
 // the new p also go into the neighbours' landing buffers, the last CTA publishes the sequence number
 // (same protocol as cg_update_p_push_kernel).
-__global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) pcg_update_p_kernel(long long n, const CGScalars* sc,
                                                            const double* __restrict__ r,
                                                            const double* __restrict__ dinv, double* __restrict__ p,
                                                            const HaloPushArgs h) {
@@ -873,7 +900,7 @@ __global__ void __launch_bounds__(128) bj_factor_kernel(const LineBlocks lb, con
 }
 
 // z = M^-1 r: forward y_j = r_j - m_j y_{j-1}, backward z_j = (y_j - c_j z_{j+1}) / d'_j  (y kept in z)
-__global__ void __launch_bounds__(128) bj_solve_kernel(const LineBlocks lb, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(128) bj_solve_kernel(const LineBlocks lb, const CGScalars* sc,
                                                        const double* __restrict__ m, const double* __restrict__ invd,
                                                        const double* __restrict__ c, const double* __restrict__ r,
                                                        double* __restrict__ z) {
@@ -896,7 +923,7 @@ __global__ void __launch_bounds__(128) bj_solve_kernel(const LineBlocks lb, cons
 
 // Generic pieces for operators without a fused entry point (any SpmvOperator with run_device):
 // partial dot, r = b - Ap with p = r and r.r
-__global__ void __launch_bounds__(256) dot_partials_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) dot_partials_kernel(long long n, const CGScalars* sc,
                                                            const double* __restrict__ x, const double* __restrict__ y,
                                                            const TailArgs tail) {
     __shared__ double scratch[8];
@@ -992,7 +1019,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloPushArgs a) {
 // last `halo` elements store them straight into the neighbours' landing buffers over NVLink.  The
 // last CTA to finish (device-scope counter after a system fence) release-stores the arrival epoch
 // into both neighbours' flags.  One launch less on the critical path than K3 + halo_push_kernel.
-__global__ void __launch_bounds__(256) cg_update_p_push_kernel(long long n, const CGScalars* __restrict__ sc,
+__global__ void __launch_bounds__(256) cg_update_p_push_kernel(long long n, const CGScalars* sc,
                                                                const double* __restrict__ r, double* __restrict__ p,
                                                                const HaloPushArgs h) {
     griddep_wait();

@@ -31,7 +31,14 @@
 
 namespace b200 {
 
-enum { ST_PLAIN = 0, ST_DOT = 1, ST_RESID = 2, ST_FUSED = 3 };
+// ST_FUSED retires ONE pending x update per launch (x += alpha_{k-1} p_{k-1}).  The x stream (8 B read + 8 B
+// written per row) can be amortised: ST_FUSED_X0 leaves x alone, ST_FUSED_X<m> retires the m pending updates
+// of the last m iterations in one read-modify-write of x, oldest first (same fma chain as m separate
+// updates: bit-identical), reading m-1 older directions next to the p_old it needs anyway.
+enum { ST_PLAIN = 0, ST_DOT = 1, ST_RESID = 2, ST_FUSED = 3, ST_FUSED_X0 = 4, ST_FUSED_X2 = 5, ST_FUSED_X3 = 6, ST_FUSED_X4 = 7 };
+__host__ __device__ constexpr bool st_fused(int mode) { return mode >= ST_FUSED; }
+__host__ __device__ constexpr int st_nx(int mode) { return mode == ST_FUSED ? 1 : (mode >= ST_FUSED_X2 ? mode - 3 : 0); }
+constexpr int ST_MAX_NX = 4;
 
 struct Stencil5Args {
     const int* row_ptr;    // local, rebased to 0 (boundary rows only)
@@ -68,7 +75,35 @@ struct Stencil5Args {
     double* xs;            // solution vector: xs += alpha * p_old
     const double* ab;      // device scalars: ab[0] = alpha (of the previous iteration), ab[1] = beta
     const uint32_t* epoch_ptr;  // if set: the halo sequence number to wait for is read from here
+    // ST_FUSED_X<m>: xp[k] = direction p_{it-2-k} (k < m-1), alpha_hist[j & 7] = alpha of iteration j,
+    // *iter_ptr = it (iterations completed so far)
+    const double* xp[ST_MAX_NX - 1];
+    const double* alpha_hist;
+    const int* iter_ptr;
 };
+
+// alphas of the pending x updates: al[k] belongs to p_{it-1-k}
+template <int MODE>
+struct XAlphas {
+    double al[st_nx(MODE) > 0 ? st_nx(MODE) : 1];
+    __device__ __forceinline__ void load(const Stencil5Args& a) {
+        constexpr int NX = st_nx(MODE);
+        if (NX >= 1) al[0] = a.ab[0];
+        if (NX >= 2) {
+            const int it = *a.iter_ptr;
+#pragma unroll
+            for (int k = 1; k < NX; k++) al[k] = a.alpha_hist[(it - 1 - k) & 7];
+        }
+    }
+};
+// x after the pending updates, oldest first; xv = x[lr], pold = p_{it-1}[lr]
+template <int MODE>
+__device__ __forceinline__ double retire_x(const Stencil5Args& a, const XAlphas<MODE>& xa, long long lr, double xv, double pold) {
+    constexpr int NX = st_nx(MODE);
+#pragma unroll
+    for (int k = NX - 1; k >= 1; k--) xv = fma(xa.al[k], __ldg(a.xp[k - 1] + lr), xv);
+    return fma(xa.al[0], pold, xv);
+}
 
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, int* error_word) {
     const uint64_t t0 = globaltimer_ns();
@@ -88,9 +123,9 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch, 
 template <int MODE, bool CG_LOADS>
 __device__ __forceinline__ double x_at(const Stencil5Args& a, long long idx, double beta = 0.0, double* po = nullptr) {
     const double* p;
-    if (MODE == ST_FUSED && po) *po = 0.0;
+    if (st_fused(MODE) && po) *po = 0.0;
     if (idx >= 0 && idx < a.n_local) {
-        if (MODE == ST_FUSED) {
+        if (st_fused(MODE)) {
             const double pold = __ldg(a.x + idx);
             if (po) *po = pold;
             return fma(beta, pold, __ldg(a.r + idx));
@@ -108,7 +143,7 @@ __device__ __forceinline__ double x_at(const Stencil5Args& a, long long idx, dou
 
 // One boundary row: CSR walk, reference order (spmv_stencil_csr_direct.cu:113-119).
 template <int MODE, bool CG_LOADS>
-__device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long r, double alpha, double beta) {
+__device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long r, const XAlphas<MODE>& xa, double beta) {
     const long long lr = r - a.row_offset;
     long long s, e;
     if (a.row_ptr != nullptr) { s = a.row_ptr[lr]; e = a.row_ptr[lr + 1]; }
@@ -123,11 +158,11 @@ __device__ __forceinline__ double boundary_row(const Stencil5Args& a, long long 
         if (c == r) xc = xv;
         sum = fma(a.values[k], xv, sum);
     }
-    if (MODE == ST_FUSED) {  // this thread owns row r: retire x, publish the new p
+    if (st_fused(MODE)) {  // this thread owns row r: retire x, publish the new p
         const double pold = a.x[lr];
         xc = fma(beta, pold, a.r[lr]);
         a.y2[lr] = xc;
-        a.xs[lr] = fma(alpha, pold, a.xs[lr]);
+        if (st_nx(MODE) > 0) a.xs[lr] = retire_x<MODE>(a, xa, lr, a.xs[lr], pold);
         a.y[lr] = sum;
         return xc * sum;
     }
@@ -156,7 +191,9 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc = 0.0;
-    const double alpha = (MODE == ST_FUSED) ? a.ab[0] : 0.0, beta = (MODE == ST_FUSED) ? a.ab[1] : 0.0;
+    const double beta = st_fused(MODE) ? a.ab[1] : 0.0;
+    XAlphas<MODE> xa;
+    xa.load(a);
     // the halo sequence number to wait for is only read where a wait happens (no live register elsewhere)
     auto wanted = [&]() -> uint32_t { return (a.epoch_ptr != nullptr) ? __ldcg(a.epoch_ptr) : a.epoch; };
 
@@ -177,7 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
             else if (t < 2LL * n) r = (long long)(n - 1) * n + (t - n);    // grid row n-1
             else if (t < 2LL * n + (n - 2)) r = (t - 2LL * n + 1) * n;     // column 0
             else r = (t - 2LL * n - (n - 2) + 1) * n + (n - 1);            // column n-1
-            if (r >= a.row_offset && r < a.row_offset + a.n_local) acc = boundary_row<MODE, CG_LOADS>(a, r, alpha, beta);
+            if (r >= a.row_offset && r < a.row_offset + a.n_local) acc = boundary_row<MODE, CG_LOADS>(a, r, xa, beta);
         }
     } else {
         // ------------------------------------------------------------ interior fast path
@@ -285,12 +322,12 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 for (int c = 0; c < COLS; c++) {
                     const int j = j0 + lane + 32 * c;
                     po[c] = 0.0;
-                    if (MODE == ST_FUSED) xr[c] = (j <= n - 1) ? raw_at(rb + col_base + 32 * c, po[c]) : 0.0;
+                    if (st_fused(MODE)) xr[c] = (j <= n - 1) ? raw_at(rb + col_base + 32 * c, po[c]) : 0.0;
                     else xr[c] = (j <= n - 1) ? x_at<MODE, CG_LOADS>(a, rb + col_base + 32 * c) : 0.0;
                 }
                 er = 0.0;
                 pe = 0.0;
-                if (MODE == ST_FUSED) {
+                if (st_fused(MODE)) {
                     if (lane == 0) er = raw_at(rb + j0 - 1 - off, pe);
                     if (lane == 31 && j0 + W <= n - 1) er = raw_at(rb + j0 + W - off, pe);
                 } else {
@@ -299,7 +336,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 }
             };
             auto finish_row = [&](double (&xr)[COLS], double& er, const double (&po)[COLS], double pe) {
-                if (MODE == ST_FUSED) {  // raw -> p = fma(beta, p_old, r); halo / padding: fma(beta, 0, v) = v
+                if (st_fused(MODE)) {  // raw -> p = fma(beta, p_old, r); halo / padding: fma(beta, 0, v) = v
 #pragma unroll
                     for (int c = 0; c < COLS; c++) xr[c] = fma(beta, po[c], xr[c]);
                     er = fma(beta, pe, er);
@@ -316,7 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 finish_row(xC, eC, poC, dpe);
             }
             load_row(i0 + 1, xS, eS, poS, peF);
-            if (MODE != ST_FUSED) {
+            if (!st_fused(MODE)) {
                 // nothing: xS is final
             } else {
                 // keep row i0+1 raw in the F registers: it is finished at the top of the first turn
@@ -332,7 +369,7 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                 if (i + STAGES - 1 < i1) issue(i + STAGES - 1);
 
                 double xsv[COLS];
-                if (MODE == ST_FUSED) {
+                if (st_fused(MODE)) {
                     // row i+1 was loaded one turn ago: finish it, then reuse the F registers for row i+2
 #pragma unroll
                     for (int c = 0; c < COLS; c++) { xS[c] = xF[c]; poS[c] = poF[c]; }
@@ -342,7 +379,8 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
 #pragma unroll
                     for (int c = 0; c < COLS; c++) {
                         const long long r = (long long)i * n + j0 + lane + 32 * c;
-                        xsv[c] = (j0 + lane + 32 * c <= n - 2 && r >= off && r < off + nl) ? a.xs[r - off] : 0.0;
+                        if (st_nx(MODE) > 0)
+                            xsv[c] = (j0 + lane + 32 * c <= n - 2 && r >= off && r < off + nl) ? a.xs[r - off] : 0.0;
                     }
                 } else {
                     double dpo[COLS], dpe;
@@ -406,16 +444,17 @@ __global__ void __launch_bounds__(WARPS * 32) stencil5_kernel(const Stencil5Args
                                 acc = fma(rv, rv, acc);
                             } else {
                                 a.y[lr] = t;
-                                if (MODE == ST_DOT || MODE == ST_FUSED) acc = fma(xC[c], t, acc);
-                                if (MODE == ST_FUSED) {
-                                    a.y2[lr] = xC[c];                          // the new p, written once
-                                    a.xs[lr] = fma(alpha, poC[c], xsv[c]);     // x += alpha p_old, deferred
+                                if (MODE == ST_DOT || st_fused(MODE)) acc = fma(xC[c], t, acc);
+                                if (st_fused(MODE)) {
+                                    a.y2[lr] = xC[c];  // the new p, written once
+                                    // x += alpha p_old (+ the older pending updates), deferred
+                                    if (st_nx(MODE) > 0) a.xs[lr] = retire_x<MODE>(a, xa, lr, xsv[c], poC[c]);
                                 }
                             }
                         }
                     }
                 }
-                if (MODE == ST_FUSED) {
+                if (st_fused(MODE)) {
 #pragma unroll
                     for (int c = 0; c < COLS; c++) { xN[c] = xC[c]; xC[c] = xS[c]; poC[c] = poS[c]; }
                     eC = eS;

@@ -107,8 +107,16 @@ int alloc_block(int dev, void** out) {
 
 }  // namespace
 
-namespace { extern int g_schedule; int g_precond = 1; }
+#ifndef B200_CG_XDEPTH_DEFAULT
+#define B200_CG_XDEPTH_DEFAULT 4
+#endif
+namespace { extern int g_schedule; extern int g_xdepth; int x_depth(); int g_precond = 1; }
 extern "C" void b200_cg_set_schedule(int deferred_x) { g_schedule = deferred_x ? 1 : 0; }
+extern "C" int b200_cg_set_xdepth(int depth) {
+    const int old = x_depth();
+    if (depth >= 1 && depth <= 4) g_xdepth = depth;
+    return old;
+}
 // preconditioner of pcg_solve_device / pcg_solve_mgpu_partitioned: 1 = Jacobi (default), 2 = block-Jacobi with
 // one tridiagonal block per grid row ("line" blocks, clipped to the rank's band)
 extern "C" int b200_pcg_set_preconditioner(int kind) {
@@ -197,6 +205,8 @@ struct RankWs {
     DeviceBand band;
     bool own_band = false;
     double *x = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *Ap = nullptr, *b = nullptr;
+    double* pmore[3] = {nullptr, nullptr, nullptr};  // direction buffers 3..5 (x retirement depth 2..4), on first use
+    double* dirbuf(int k) const { return k == 0 ? p : k == 1 ? p2 : pmore[k - 2]; }
     // reduction context: per-CTA partials (two sums), group sums, tickets, local totals, results
     double *partials = nullptr, *partials2 = nullptr, *gsum = nullptr, *stash = nullptr, *sums = nullptr;
     uint32_t* tickets = nullptr;
@@ -212,6 +222,7 @@ struct RankWs {
 
     void free_vectors() {
         cudaFree(x); cudaFree(r); cudaFree(p); cudaFree(p2); cudaFree(Ap); cudaFree(b);
+        for (auto& q : pmore) { cudaFree(q); q = nullptr; }
         cudaFree(partials); cudaFree(partials2); cudaFree(gsum); cudaFree(tickets); cudaFree(stash); cudaFree(sums);
         cudaFree(scalars);
         cudaFree(dinv); cudaFree(dinv_err);
@@ -310,6 +321,18 @@ SolveOut g_last;  // per-phase event times of the most recent solve (enable_deta
 // deferred-x schedule (2 launches, 112 B/row per iteration) unless B200_CG_SCHEDULE=classic or
 // b200_cg_set_schedule(0)
 int g_schedule = -1;
+// x retirement depth of the deferred-x schedule on the STENCIL5 path: the SpMV launch of every `depth`-th
+// iteration retires the last `depth` x updates in one read-modify-write of x (depth + 1 direction buffers):
+// (96 + 8 + 8 / depth) B/row per iteration -- 112 / 108 / 106.7 / 106 for depth 1 / 2 / 3 / 4.
+int g_xdepth = -1;
+int x_depth() {
+    if (g_xdepth < 0) {
+        const char* e = getenv("B200_CG_XDEPTH");
+        const int v = e ? atoi(e) : B200_CG_XDEPTH_DEFAULT;
+        g_xdepth = (v >= 1 && v <= 4) ? v : B200_CG_XDEPTH_DEFAULT;
+    }
+    return g_xdepth;
+}
 bool schedule_deferred_x() {
     if (g_schedule < 0) {
         const char* e = getenv("B200_CG_SCHEDULE");
@@ -529,6 +552,10 @@ struct Engine {
             if (combine(B200_RED_RZ0, 0)) return 1;
         }
         const bool dx = fused && schedule_deferred_x() && !pcg;
+        const int xd = (dx && b200_cg_get_kernel() == 1) ? x_depth() : 1, nbuf = xd + 1;  // ring kernels: depth 1 only
+        if (dx)
+            for (int k = 2; k < nbuf; k++)
+                if (!w.pmore[k - 2]) B200_CUDA(cudaMalloc(&w.pmore[k - 2], (size_t)w.nl * sizeof(double)));
         // operators without a fused SpMV: same idea one level down -- x is retired inside the p update (K3x)
         const bool px = !fused && schedule_deferred_x() && !pcg;
         if (multi) {
@@ -557,13 +584,18 @@ struct Engine {
             Nvtx range_iter("CG_Iteration");
             nvtxRangePushA("SpMV");
             if (dx) {
-                // direction k lives in p (k even) or p2 (k odd)
-                double* pcur = (it & 1) ? w.p2 : w.p;
-                double* pold = (it & 1) ? w.p : w.p2;
+                // direction k lives in direction buffer k % nbuf; every xd-th launch retires the xd pending x updates
+                double* pcur = w.dirbuf(it % nbuf);
                 b200_band band;
                 wire_band_dir(w, &band, it);  // halo copies of direction `it` (kept by b200_cg_halo_dir)
-                if (it == 0) B200_K(b200_cg_spmv_dot(&band, pcur, w.Ap, &ctx, w.st));
-                else B200_K(b200_cg_spmv_fused(&band, pold, w.r, pcur, w.x, w.Ap, &ctx, w.st));
+                if (it == 0) {
+                    B200_K(b200_cg_spmv_dot(&band, pcur, w.Ap, &ctx, w.st));
+                } else {
+                    const int nx = (it % xd == 0) ? xd : 0;
+                    const double* older[3] = {nullptr, nullptr, nullptr};
+                    for (int k = 0; k + 1 < nx; k++) older[k] = w.dirbuf((it - 2 - k) % nbuf);
+                    B200_K(b200_cg_spmv_fused_nx(&band, w.dirbuf((it - 1) % nbuf), older, nx, w.r, pcur, w.x, w.Ap, &ctx, w.st));
+                }
             } else if (fused) {
                 b200_band band;
                 wire_band(w, &band);
@@ -654,7 +686,9 @@ struct Engine {
         }
         if (dx) {
             // the x update of the last completed iteration is still pending: x += alpha p_last
-            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p2, w.x, 0, w.st));
+            const double* bufs[5];
+            for (int k = 0; k < nbuf; k++) bufs[k] = w.dirbuf(k);
+            B200_K(b200_cg_finish_x_depth(w.nl, w.scalars, bufs, nbuf, xd, 0, w.x, w.st));
             mark(T_P);
         } else if (px) {
             // pending only if the convergence test stopped the loop in front of K3x

@@ -91,6 +91,10 @@ int b200_spmv_stencil5_ellpack(const double* d_values, const int* d_col_indices,
 /* kernel behind b200_stencil5_spmv when a band asks for the default: 0 = bulk-copy ring (csrc/stencil5.cuh),
  * 20 / 21 / 22 = sequential sweep with 1 / 2 / 4 rows per thread (csrc/stencil5_direct.cuh) */
 void b200_stencil5_set_plain_variant(int v);
+/* kernel family of the fused CG passes: 0 = bulk-copy ring, 1 = sequential sweep (default; env
+ * B200_CG_KERNEL=ring|sweep).  The ring family retires x once per launch only (x depth 1). */
+void b200_cg_set_kernel(int sweep);
+int b200_cg_get_kernel(void);
 /* number of per-CTA partial sums the fused kernels below write for this band */
 int b200_stencil5_num_partials(const b200_band* band);
 /* human-readable description of tuning variant v (NULL past the last one) */
@@ -253,6 +257,19 @@ int b200_cg_update_p_push(long long n, const void* d_scalars, const double* d_r,
  * Every iterate is bit-identical to the classic K1 / K2 / K3 schedule.                          */
 int b200_cg_spmv_fused(const b200_band* band, const double* d_p_old, const double* d_r, double* d_p_new,
                        double* d_x, double* d_Ap, const b200_reduce_ctx* ctx, b200_stream stream);
+/* The same pass with the x stream amortised over `depth` iterations (depth <= 4, depth + 1 direction buffers,
+ * direction j in buffer j % (depth + 1)): nx = 0 leaves x alone, nx = m retires the m pending updates
+ *   x = fma(alpha_{it-1}, p_{it-1}, ... fma(alpha_{it-m}, p_{it-m}, x))       (oldest first: bit-identical to
+ * m separate axpy_kernel_device launches, cg_solver.cu:59-66) in ONE read-modify-write of x;
+ * d_p_older[k] = p_{it-2-k}, k < nx - 1.  alpha history: kept by the p.Ap tail in the scalar block.
+ * b200_cg_finish_x_depth retires what is still pending after the last iteration. */
+int b200_cg_spmv_fused_nx(const b200_band* band, const double* d_p_old, const double* const* d_p_older, int nx,
+                          const double* d_r, double* d_p_new, double* d_x, double* d_Ap,
+                          const b200_reduce_ctx* ctx, b200_stream stream);
+int b200_cg_finish_x_depth(long long n, const void* d_scalars, const double* const* d_pbuf, int nbuf, int depth,
+                           int only_if_converged, double* d_x, b200_stream stream);
+/* x retirement depth of the deferred-x schedule (1..4, env B200_CG_XDEPTH); returns the previous value */
+int b200_cg_set_xdepth(int depth);
 int b200_cg_update_r(long long n, const double* d_Ap, double* d_r, const b200_halo_push_args* push,
                      const b200_reduce_ctx* ctx, b200_stream stream);
 int b200_cg_halo_dir(const double* d_r_prev, const double* d_r_next, const double* d_pold_prev,

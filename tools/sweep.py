@@ -128,6 +128,24 @@ def main():
                     ms, best = timeit(lambda: B.check(L.b200_cg_spmv_fused(C.byref(band), dptr(x), dptr(fr), dptr(fp),
                                                                            dptr(fx), dptr(y), C.byref(ctx), s), "fused"))
                     rec("stencil5_fused(K1F)+tail", ms, best, 8.0 * nnz + 48.0 * N, variant=v, rows_per_item=R)
+        if "cgsweep" in what:  # fused CG passes, ring against sequential sweep, by number of x updates retired per launch
+            band = B.Band(rp.data_ptr(), ci.data_ptr(), va.data_ptr(), nnz + 2, 0, N, n, 0, None, None, None,
+                          None, 0, 4, 0)
+            fr, fp, fx = (torch.ones(N, dtype=torch.float64, device="cuda") for _ in range(3))
+            older_t = [torch.ones(N, dtype=torch.float64, device="cuda") for _ in range(3)]
+            older = (C.c_void_p * 3)(*[t.data_ptr() for t in older_t])
+            for fam, name in ((0, "ring"), (1, "sweep")):
+                L.b200_cg_set_kernel(fam)
+                ms, best = timeit(lambda: B.check(L.b200_cg_spmv_dot(C.byref(band), dptr(x), dptr(y), C.byref(ctx), s), "dot"))
+                rec(name + "_dot+tail", ms, best, st_bytes)
+                for nx in (0, 1, 2, 3, 4):
+                    if fam == 0 and nx > 2:
+                        continue
+                    ms, best = timeit(lambda: B.check(L.b200_cg_spmv_fused_nx(C.byref(band), dptr(x), older, nx, dptr(fr), dptr(fp),
+                                                                              dptr(fx), dptr(y), C.byref(ctx), s), "fused"))
+                    nb = 8.0 * nnz + 32.0 * N + (16.0 * N + 8.0 * N * (nx - 1) if nx > 0 else 0.0)
+                    rec("%s_fused_x%d(K1F)+tail" % (name, nx), ms, best, nb)
+            L.b200_cg_set_kernel(0)
         del ctx
 
     if "cg" in what:
