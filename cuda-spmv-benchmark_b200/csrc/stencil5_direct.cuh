@@ -107,7 +107,10 @@ __global__ void __launch_bounds__(256) stencil5_direct_kernel(const Stencil5Args
 // Band mode: tiles that read a halo wait for the neighbour's arrival word and are mapped to the LAST CTAs of
 // the grid (the mapping is keyed on the halo pointers, not on the flags, so that the order of the partial
 // sums does not depend on whether a launch has to wait).
-constexpr int SWEEP_TILES = 4;
+#ifndef B200_SWEEP_TILES
+#define B200_SWEEP_TILES 2
+#endif
+constexpr int SWEEP_TILES = B200_SWEEP_TILES;
 
 template <int MODE, bool CG_LOADS>
 __device__ __forceinline__ double sweep_row_generic(const Stencil5Args& a, long long lr, const XAlphas<MODE>& xa, double beta) {
@@ -140,11 +143,14 @@ template <int MODE, bool CG_LOADS>
 __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args a) {
     __shared__ double warp_part[8];
     griddep_wait();
-    if (a.converged != nullptr && *a.converged != 0) return;
-    const unsigned int nloc = (unsigned int)a.n_local, n = (unsigned int)a.n;
+    // the scalars of this launch are loaded together, in front of the branch on the first of them: one
+    // global-memory latency per CTA instead of two (a CTA lives for a few microseconds only)
+    const int conv = (a.converged != nullptr) ? *a.converged : 0;
     const double beta = st_fused(MODE) ? a.ab[1] : 0.0;
     XAlphas<MODE> xa;
     xa.load(a);
+    if (conv != 0) return;
+    const unsigned int nloc = (unsigned int)a.n_local, n = (unsigned int)a.n;
     constexpr unsigned int ROWS_PER_CTA = 256u * SWEEP_TILES;
     // logical CTA: the CTAs that cover the first grid row of a band with a halo run last
     unsigned int cta = blockIdx.x;

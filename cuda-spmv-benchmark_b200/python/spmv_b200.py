@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libspmv_b200.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(PKG_DIR, "libspmv_b200.so")  # B200_LIB_PATH: A/B builds of the same sources
 REPO_ROOT = os.path.dirname(PKG_DIR)
 
 
