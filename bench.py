@@ -527,7 +527,11 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": k1_name, "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "frac": (achieved / peak) if achieved else None,
+                     "frac_of_nominal_7700GBs": (achieved / 7700.0) if achieved else None,
+                     "peak_note": "the measured peak is a device copy (50 % writes); this launch mix writes 24 % of its bytes, "
+                                  "so frac can exceed 1 (tools/sweep.py: plain SpMV, 14 % writes, reaches 7.2 TB/s)",
+                     "traffic": traffic,
                      "bytes_per_launch": k1_bytes, "traffic_kernel_algorithmic_bytes": traffic_alg,
                      "avg_launch_ms": k1_avg_ms, "launches_timed": k1_cnt},
         "spmv": {"ms": k1_avg_ms, "gb_s": achieved, "note": "per-GPU fused SpMV launch inside CG (see roofline.kernel)"},

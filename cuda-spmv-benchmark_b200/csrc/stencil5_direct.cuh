@@ -107,6 +107,28 @@ __global__ void __launch_bounds__(256) stencil5_direct_kernel(const Stencil5Args
 // Band mode: tiles that read a halo wait for the neighbour's arrival word and are mapped to the LAST CTAs of
 // the grid (the mapping is keyed on the halo pointers, not on the flags, so that the order of the partial
 // sums does not depend on whether a launch has to wait).
+// A/B switches (tools: build a second library with -D..., load it with B200_LIB_PATH): streaming stores for the
+// result vectors, evict-first loads for the coefficient stream
+#ifndef B200_SWEEP_STCS
+#define B200_SWEEP_STCS 0
+#endif
+#ifndef B200_SWEEP_LDCS
+#define B200_SWEEP_LDCS 0
+#endif
+__device__ __forceinline__ void sweep_store(double* p, double v) {
+#if B200_SWEEP_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ double sweep_coef(const double* p) {
+#if B200_SWEEP_LDCS
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
 #ifndef B200_SWEEP_TILES
 #define B200_SWEEP_TILES 2
 #endif
@@ -185,7 +207,7 @@ __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args 
         if (interior && lr >= n && lr + n < nloc) {
             // ---------------------------------------------------------------- every neighbour is a local element
             const double* v = a.values + (a.base0 + (long long)i * a.row_stride + 5 * (long long)j);
-            const double vN = __ldg(v), vW = __ldg(v + 1), vC = __ldg(v + 2), vE = __ldg(v + 3), vS = __ldg(v + 4);
+            const double vN = sweep_coef(v), vW = sweep_coef(v + 1), vC = sweep_coef(v + 2), vE = sweep_coef(v + 3), vS = sweep_coef(v + 4);
             double xW, xC, xE, xN, xS, poC = 0.0;
             if (st_fused(MODE)) {
                 const double* pr = a.r + lr;
@@ -208,14 +230,14 @@ __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args 
             t = fma(vS, xS, t);
             if (MODE == ST_RESID) {
                 const double rv = __ldg(a.b + lr) - t;
-                a.y[lr] = rv;
-                a.y2[lr] = rv;
+                sweep_store(a.y + lr, rv);
+                sweep_store(a.y2 + lr, rv);
                 acc = fma(rv, rv, acc);
             } else {
-                a.y[lr] = t;
+                sweep_store(a.y + lr, t);
                 if (st_fused(MODE)) {
-                    a.y2[lr] = xC;
-                    if (st_nx(MODE) > 0) a.xs[lr] = retire_x<MODE>(a, xa, lr, a.xs[lr], poC);
+                    sweep_store(a.y2 + lr, xC);
+                    if (st_nx(MODE) > 0) sweep_store(a.xs + lr, retire_x<MODE>(a, xa, lr, a.xs[lr], poC));
                 }
                 if (MODE != ST_PLAIN) acc = fma(xC, t, acc);
             }
