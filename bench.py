@@ -48,6 +48,8 @@ def parse():
                     help="CPU arm: run (and report) this grid instead of --grid (0 = --grid, reduced only if host RAM is short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operators", action="store_true", help="skip the 10k x 10k operator comparison (configs[1])")
+    ap.add_argument("--no-weak-leg", action="store_true",
+                    help="N > 1 at the default grid: skip the short weak-scaling measurement (configs[4]) added to the line")
     ap.add_argument("--single-process", action="store_true",
                     help="N > 1 without torchrun: ONE process drives all N GPUs (one enqueue thread per GPU), the "
                          "north-star topology / the reference CLI's `cg_solver_mgpu_stencil`")
@@ -265,6 +267,58 @@ def operator_table(L, B, torch, peak, n=10000, reps=10, warm=5):
     ms = timed(lambda: B.check(L.b200_spmv_stencil5_ellpack(dp(val), dp(idx), dp(x), dp(y), N, 5, 1.0, 0.0, n, s), "st-ell"))
     out["stencil5-ellpack"] = row(ms, 56.0 * N, y)
     return out
+
+
+def weak_leg(L, B, torch, dist, world, rank, local_rank, single, barrier):
+    """configs[4] inside the strong-scaling line: 20000^2 rows PER GPU (reference recipe
+    scripts/benchmarking/benchmark_weak_scaling.sh:15-21, square grids n0*sqrt(P)), 1 warm-up + 3 timed solves
+    through the same public entry point.  The exchange blocks are re-created for the larger grid."""
+    import math
+    import mgpu_bootstrap
+    step = 2 * world
+    n = int(round(20000 * math.sqrt(world) / step)) * step
+    N = n * n
+    L.b200_mgpu_finalize()
+    if single:
+        devs = (C.c_int * world)(*range(world))
+        if L.b200_mgpu_init_single_process(world, devs, n) != 0:
+            raise RuntimeError("b200_mgpu_init_single_process failed")
+        nl, off = N, 0
+    else:
+        mgpu_bootstrap.connect(L, dist, rank, world, local_rank, n)
+        nl, off = mgpu_bootstrap.partition(N, world, rank)
+    mat = B.HostMatrix.synthetic_stencil(n)
+    b_host = torch.full((nl,), 1.0, dtype=torch.float64).pin_memory()
+    x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
+    stats = B.CGStatsMultiGPU()
+    cfg = B.cg_config(MAX_ITERS, TOL, 0, 0)
+    times, kats = [], []
+    for step_i in range(4):
+        x_host.zero_()
+        barrier()
+        rc = L.cg_solve_mgpu_partitioned(None, mat.ptr(), b_host.data_ptr() - off * 8, x_host.data_ptr() - off * 8, cfg,
+                                         C.byref(stats))
+        barrier()
+        if rc != 0 or not stats.converged:
+            raise RuntimeError("weak-scaling solve failed rc=%d" % rc)
+        d = stats.time_total_ms
+        if dist is not None:
+            t = torch.tensor([d], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d = float(t[0])
+        if step_i > 0:
+            times.append(d)
+            kats.append((stats.iterations, stats.residual_norm, stats.solution_sum))
+    if len(set(kats)) != 1:
+        raise RuntimeError("weak-scaling solves are not bit-reproducible")
+    ms = sum(times) / len(times)
+    rows_rank0 = mgpu_bootstrap.partition(N, world, 0)[0]
+    return {"config": "20000^2 rows per GPU (BASELINE.json configs[4])", "grid": n, "rows": N, "rows_per_gpu": rows_rank0,
+            "iterations": stats.iterations, "ms": round(ms, 4), "ms_steps": [round(v, 3) for v in times],
+            "ms_per_iteration": round(ms / stats.iterations, 4), "warmup": 1, "steps": 3,
+            "solution_sum": stats.solution_sum, "residual_norm": stats.residual_norm,
+            "note": "device-timed, max over ranks; compare ms_per_iteration with the one-GPU 20000^2 line (value / 14): "
+                    "equal per-GPU work, weak-scaling efficiency = that ratio"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -626,6 +680,15 @@ def run_b200(args):
         v = cpu.solve()
         line["cpu_baseline"] = {"value": v, "unit": "ms", "cores": cpu.threads, "kind": "port", "grid": cpu.n,
                                 "workload": cpu.workload(), "sample": cpu.sample(1, v)}
+    if world > 1 and not single and not args.weak and not args.no_weak_leg and n == 20000:
+        del b_host, x_host
+        for p_ in near_ptrs:
+            L.b200_host_free(p_)
+        near_ptrs.clear()
+        try:
+            line["weak_scaling"] = weak_leg(L, B, torch, dist, world, rank, local_rank, single, barrier)
+        except Exception as e:  # the leg is an extra: never lose the strong-scaling line over it
+            line["weak_scaling"] = {"error": str(e)[:300]}
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
