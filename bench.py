@@ -269,27 +269,39 @@ def operator_table(L, B, torch, peak, n=10000, reps=10, warm=5):
     return out
 
 
-def weak_leg(L, B, torch, dist, world, rank, local_rank, single, barrier):
+def weak_leg(L, B, torch, dist, world, rank, local_rank, barrier):
     """configs[4] inside the strong-scaling line: 20000^2 rows PER GPU (reference recipe
     scripts/benchmarking/benchmark_weak_scaling.sh:15-21, square grids n0*sqrt(P)), 1 warm-up + 3 timed solves
-    through the same public entry point.  The exchange blocks are re-created for the larger grid."""
+    through the same public entry point.  The exchange blocks are re-created for the larger grid.
+    Every step that can fail on one rank is followed by a MAX all-reduce of the failure flag, so that all ranks
+    leave together (a rank that raised alone would leave the others in a collective)."""
     import math
     import mgpu_bootstrap
+
+    def agree(failed, what):
+        t = torch.tensor([1.0 if failed else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if float(t[0]) != 0.0:
+            raise RuntimeError("weak-scaling leg: %s failed on some rank" % what)
+
     step = 2 * world
     n = int(round(20000 * math.sqrt(world) / step)) * step
     N = n * n
     L.b200_mgpu_finalize()
-    if single:
-        devs = (C.c_int * world)(*range(world))
-        if L.b200_mgpu_init_single_process(world, devs, n) != 0:
-            raise RuntimeError("b200_mgpu_init_single_process failed")
-        nl, off = N, 0
-    else:
-        mgpu_bootstrap.connect(L, dist, rank, world, local_rank, n)
-        nl, off = mgpu_bootstrap.partition(N, world, rank)
-    mat = B.HostMatrix.synthetic_stencil(n)
-    b_host = torch.full((nl,), 1.0, dtype=torch.float64).pin_memory()
-    x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
+    handle = (C.c_ubyte * mgpu_bootstrap.HANDLE_BYTES)()
+    agree(L.b200_mgpu_init_rank(rank, world, local_rank, n, handle) != 0, "b200_mgpu_init_rank")
+    raw = mgpu_bootstrap.all_gather_handles(dist, bytes(handle), "cuda")
+    agree(L.b200_mgpu_connect((C.c_ubyte * len(raw)).from_buffer_copy(raw)) != 0, "b200_mgpu_connect")
+    nl, off = mgpu_bootstrap.partition(N, world, rank)
+    mat = b_host = x_host = None
+    try:
+        mat = B.HostMatrix.synthetic_stencil(n)
+        b_host = torch.full((nl,), 1.0, dtype=torch.float64).pin_memory()
+        x_host = torch.zeros(nl, dtype=torch.float64).pin_memory()
+        ok = True
+    except Exception:
+        ok = False
+    agree(not ok, "host buffer allocation")
     stats = B.CGStatsMultiGPU()
     cfg = B.cg_config(MAX_ITERS, TOL, 0, 0)
     times, kats = [], []
@@ -298,19 +310,16 @@ def weak_leg(L, B, torch, dist, world, rank, local_rank, single, barrier):
         barrier()
         rc = L.cg_solve_mgpu_partitioned(None, mat.ptr(), b_host.data_ptr() - off * 8, x_host.data_ptr() - off * 8, cfg,
                                          C.byref(stats))
-        barrier()
-        if rc != 0 or not stats.converged:
-            raise RuntimeError("weak-scaling solve failed rc=%d" % rc)
-        d = stats.time_total_ms
-        if dist is not None:
-            t = torch.tensor([d], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            d = float(t[0])
+        torch.cuda.synchronize()
+        t = torch.tensor([stats.time_total_ms, 1.0 if (rc != 0 or not stats.converged) else 0.0], dtype=torch.float64,
+                         device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if float(t[1]) != 0.0:
+            raise RuntimeError("weak-scaling leg: a solve failed on some rank (rc=%d here)" % rc)
         if step_i > 0:
-            times.append(d)
+            times.append(float(t[0]))
             kats.append((stats.iterations, stats.residual_norm, stats.solution_sum))
-    if len(set(kats)) != 1:
-        raise RuntimeError("weak-scaling solves are not bit-reproducible")
+    agree(len(set(kats)) != 1, "bit-reproducibility of the solves")
     ms = sum(times) / len(times)
     rows_rank0 = mgpu_bootstrap.partition(N, world, 0)[0]
     return {"config": "20000^2 rows per GPU (BASELINE.json configs[4])", "grid": n, "rows": N, "rows_per_gpu": rows_rank0,
@@ -686,7 +695,7 @@ def run_b200(args):
             L.b200_host_free(p_)
         near_ptrs.clear()
         try:
-            line["weak_scaling"] = weak_leg(L, B, torch, dist, world, rank, local_rank, single, barrier)
+            line["weak_scaling"] = weak_leg(L, B, torch, dist, world, rank, local_rank, barrier)
         except Exception as e:  # the leg is an extra: never lose the strong-scaling line over it
             line["weak_scaling"] = {"error": str(e)[:300]}
     if saved_stdout is not None:
