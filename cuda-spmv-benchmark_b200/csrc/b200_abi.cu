@@ -920,6 +920,30 @@ extern "C" int b200_cg_finish_x(long long n, const void* d_scalars, const double
     return b200_cg_finish_x_depth(n, d_scalars, bufs, d_p0 == d_p1 ? 1 : 2, 1, only_if_converged, d_x, stream);
 }
 
+extern "C" int b200_cg_update_px_nx(long long n, const void* d_scalars, const double* d_r, const double* d_p_old,
+                                    const double* const* d_p_older, int nx, double* d_p_new, double* d_x, b200_stream stream) {
+    if (!d_scalars || !d_r || !d_p_old || !d_p_new || (nx > 0 && !d_x) || (nx > 1 && !d_p_older))
+        return fail(B200_EINVAL, "cg_update_px_nx: NULL argument");
+    if (nx < 0 || nx > ST_MAX_NX || d_p_new == d_p_old) return fail(B200_EINVAL, "cg_update_px_nx: bad x retirement arguments");
+    UpdatePxArgs a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k + 1 < nx; k++) {
+        if (!d_p_older[k] || d_p_older[k] == d_p_new) return fail(B200_EINVAL, "cg_update_px_nx: an older direction is NULL or aliases p_new");
+        a.older[k] = d_p_older[k];
+    }
+    const int grid = blas1_grid(n, 1, kRrCtasPerSm);
+    const CGScalars* sc = static_cast<const CGScalars*>(d_scalars);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (nx) {
+        case 0: launch_plain(cg_update_px_depth_kernel<0>, grid, 256, 0, s, n, sc, d_r, d_p_old, d_p_new, d_x, a); break;
+        case 1: launch_plain(cg_update_px_depth_kernel<1>, grid, 256, 0, s, n, sc, d_r, d_p_old, d_p_new, d_x, a); break;
+        case 2: launch_plain(cg_update_px_depth_kernel<2>, grid, 256, 0, s, n, sc, d_r, d_p_old, d_p_new, d_x, a); break;
+        case 3: launch_plain(cg_update_px_depth_kernel<3>, grid, 256, 0, s, n, sc, d_r, d_p_old, d_p_new, d_x, a); break;
+        default: launch_plain(cg_update_px_depth_kernel<4>, grid, 256, 0, s, n, sc, d_r, d_p_old, d_p_new, d_x, a); break;
+    }
+    return check_launch("cg_update_px_depth_kernel");
+}
+
 extern "C" int b200_cg_update_px(long long n, const void* d_scalars, const double* d_r, double* d_p, double* d_x,
                                  b200_stream stream) {
     if (!d_scalars || !d_r || !d_p || !d_x) return fail(B200_EINVAL, "cg_update_px: NULL argument");

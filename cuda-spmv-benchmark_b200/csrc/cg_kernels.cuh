@@ -576,8 +576,9 @@ __global__ void __launch_bounds__(256) cg_halo_dir_kernel(const HaloDirArgs a) {
 // retired.  Direction j lives in pbuf[j % nbuf] (nbuf = depth + 1); the launches of iterations depth, 2 depth,
 // ... each retired the `depth` updates before them, so with c completed iterations (known on the device)
 // the pending ones are j = depth * floor((c - 1) / depth) .. c - 1, applied oldest first.
-// only_if_converged (depth 1, p0 == p1): the K3x schedule (below) retires x inside the p update of the same
-// iteration, so an update is pending only when the convergence test stopped the loop in front of that kernel.
+// only_if_converged: the K3x schedule (below) retires x inside the p update of the same iteration (or of every
+// depth-th iteration), so the update of the LAST iteration is pending only when the convergence test stopped
+// the loop in front of that kernel.
 struct FinishXArgs {
     const double* pbuf[5];
     int nbuf;
@@ -589,9 +590,11 @@ __global__ void __launch_bounds__(256) cg_finish_x_kernel(long long n, const CGS
     griddep_wait();
     const int c = sc->iterations;
     if (c <= 0) return;
-    if (a.only_if_converged && !sc->converged) return;
-    const int first = a.depth * ((c - 1) / a.depth);
-    const int cnt = c - first;  // 1 .. depth
+    // K3x schedule, solve cut off by max_iters: the K3x launch of the last iteration did run (and retired, if
+    // it was its turn), so the retired prefix is depth * floor(c / depth) -- nothing pending at depth 1
+    const int first = (a.only_if_converged && !sc->converged) ? a.depth * (c / a.depth) : a.depth * ((c - 1) / a.depth);
+    const int cnt = c - first;  // 0 .. depth
+    if (cnt <= 0) return;
     double al[4] = {0.0, 0.0, 0.0, 0.0};
     const double* p[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < 4; k++)
@@ -707,6 +710,63 @@ __global__ void __launch_bounds__(256) cg_update_px_kernel(long long n, const CG
                     x[i] = fma(alpha, po, x[i]);
                     p[i] = fma(beta, po, r[i]);
                 }
+            }
+        }
+    }
+}
+
+// K3x with the x stream amortised over `depth` iterations (the generic-operator twin of ST_FUSED_X<m>,
+// stencil5.cuh): p_new = r + beta p_old goes to a FRESH direction buffer (direction j lives in buffer
+// j mod (depth + 1)), and the launch that forms direction j with j % depth == 0 (NX = depth) retires the updates
+// of directions j - depth .. j - 1 in one read-modify-write of x, oldest first -- the same fma chain as `depth`
+// separate launches of K3x.  24 + (16 + 8 (d - 1)) / d B/row instead of 40: 34 at d = 4.
+// alpha of direction j - 1 is this iteration's alpha; the older ones come from the history the p.Ap tail keeps
+// (sc->iterations == j here: the r.r tail of this iteration has run).
+struct UpdatePxArgs {
+    const double* older[3];  // p_{j-2}, p_{j-3}, p_{j-4}
+};
+template <int NX>
+__global__ void __launch_bounds__(256) cg_update_px_depth_kernel(long long n, const CGScalars* sc,
+                                                                 const double* __restrict__ r,
+                                                                 const double* __restrict__ p_old,
+                                                                 double* __restrict__ p_new, double* __restrict__ x,
+                                                                 const UpdatePxArgs a) {
+    griddep_wait();
+    if (sc->converged) return;
+    const double beta = sc->beta;
+    double al[NX > 0 ? NX : 1];
+    if (NX >= 1) al[0] = sc->alpha;
+    if (NX >= 2) {
+        const int j = sc->iterations;
+#pragma unroll
+        for (int k = 1; k < NX; k++) al[k] = sc->alpha_hist[(j - 1 - k) & 7];
+    }
+    constexpr int UNROLL = 4;
+    const long long tile = 256LL * UNROLL;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        double pv[UNROLL], rv[UNROLL], xv[UNROLL], ov[UNROLL][NX > 1 ? NX - 1 : 1];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const long long i = base + (long long)u * 256 + threadIdx.x;
+            if (i < n) {
+                pv[u] = __ldcs(p_old + i);
+                rv[u] = __ldcs(r + i);
+                if (NX >= 1) xv[u] = __ldcs(x + i);
+#pragma unroll
+                for (int k = 1; k < NX; k++) ov[u][k - 1] = __ldcs(a.older[k - 1] + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const long long i = base + (long long)u * 256 + threadIdx.x;
+            if (i < n) {
+                if (NX >= 1) {
+                    double t = xv[u];
+#pragma unroll
+                    for (int k = NX - 1; k >= 1; k--) t = fma(al[k], ov[u][k - 1], t);
+                    x[i] = fma(al[0], pv[u], t);
+                }
+                p_new[i] = fma(beta, pv[u], rv[u]);
             }
         }
     }

@@ -553,11 +553,12 @@ struct Engine {
         }
         const bool dx = fused && schedule_deferred_x() && !pcg;
         const int xd = (dx && b200_cg_get_kernel() == 1) ? x_depth() : 1, nbuf = xd + 1;  // ring kernels: depth 1 only
-        if (dx)
-            for (int k = 2; k < nbuf; k++)
-                if (!w.pmore[k - 2]) B200_CUDA(cudaMalloc(&w.pmore[k - 2], (size_t)w.nl * sizeof(double)));
-        // operators without a fused SpMV: same idea one level down -- x is retired inside the p update (K3x)
+        // operators without a fused SpMV: same idea one level down -- x is retired inside the p update (K3x),
+        // with the same retirement depth (single GPU: the generic operators have no band form)
         const bool px = !fused && schedule_deferred_x() && !pcg;
+        const int pd = (px && !multi) ? x_depth() : 1, pbufs = pd > 1 ? pd + 1 : 1;  // depth 1: K3x updates p in place
+        for (int k = 2; k < (dx ? nbuf : pbufs); k++)
+            if (!w.pmore[k - 2]) B200_CUDA(cudaMalloc(&w.pmore[k - 2], (size_t)w.nl * sizeof(double)));
         if (multi) {
             B200_K(b200_halo_push(w.p, w.nl, &push, nullptr, w.st));
             if (!team.phase()) return 1;
@@ -602,13 +603,14 @@ struct Engine {
                 B200_K(b200_cg_spmv_dot(&band, w.p, w.Ap, &ctx, w.st));
             } else {
                 int np = 0;
-                if (operator_spmv_dot(op, w.p, w.Ap, w.partials, w.max_partials, &np, w.scalars) == 0) {
+                double* pk = w.dirbuf(it % pbufs);  // K3x with depth: direction k lives in buffer k mod (depth + 1)
+                if (operator_spmv_dot(op, pk, w.Ap, w.partials, w.max_partials, &np, w.scalars) == 0) {
                     // this library's generic CSR / ELLPACK kernels write one partial per warp item
                     B200_K(b200_cg_reduce(&ctx, B200_RED_PAP, np, 0, 3, w.st));
                 } else {
                     // foreign operator (or unaligned arrays): SpMV through the vtable, then the dot pass
-                    if (op->run_device(w.p, w.Ap) != 0) return 1;
-                    B200_K(b200_dot_partials(w.nl, w.Ap, w.p, B200_RED_PAP, &ctx, w.st));
+                    if (op->run_device(pk, w.Ap) != 0) return 1;
+                    B200_K(b200_dot_partials(w.nl, w.Ap, pk, B200_RED_PAP, &ctx, w.st));
                 }
             }
             mark(T_SPMV, it);
@@ -657,7 +659,12 @@ struct Engine {
                 Nvtx range_p(multi ? "BLAS_AXPBY+Halo_Exchange" : "BLAS_AXPBY");
                 if (bj) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.z, nullptr, w.p, multi ? &push : nullptr, w.st));      // K3: p = z + beta p
                 else if (pcg) B200_K(b200_pcg_update_p(w.nl, w.scalars, w.r, w.dinv, w.p, multi ? &push : nullptr, w.st));  // K3p
-                else if (px) B200_K(b200_cg_update_px(w.nl, w.scalars, w.r, w.p, w.x, w.st));                      // K3x
+                else if (px && pd > 1) {  // K3x forming direction j = it + 1; every pd-th one retires the pd pending x updates
+                    const int j = it + 1, nx = (j % pd == 0) ? pd : 0;
+                    const double* older[3] = {nullptr, nullptr, nullptr};
+                    for (int k = 0; k + 1 < nx; k++) older[k] = w.dirbuf((j - 2 - k) % pbufs);
+                    B200_K(b200_cg_update_px_nx(w.nl, w.scalars, w.r, w.dirbuf((j - 1) % pbufs), older, nx, w.dirbuf(j % pbufs), w.x, w.st));
+                } else if (px) B200_K(b200_cg_update_px(w.nl, w.scalars, w.r, w.p, w.x, w.st));                      // K3x
                 else if (!multi) B200_K(b200_cg_update_p(w.nl, w.scalars, w.r, w.p, w.st));                        // K3
                 else B200_K(b200_cg_update_p_push(w.nl, w.scalars, w.r, w.p, &push, w.st));  // K3 + halo push
                 if (multi && !team.phase()) return 1;
@@ -692,7 +699,13 @@ struct Engine {
             mark(T_P);
         } else if (px) {
             // pending only if the convergence test stopped the loop in front of K3x
-            B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p, w.x, 1, w.st));
+            if (pd > 1) {
+                const double* bufs[5];
+                for (int k = 0; k < pbufs; k++) bufs[k] = w.dirbuf(k);
+                B200_K(b200_cg_finish_x_depth(w.nl, w.scalars, bufs, pbufs, pd, 1, w.x, w.st));
+            } else {
+                B200_K(b200_cg_finish_x(w.nl, w.scalars, w.p, w.p, w.x, 1, w.st));
+            }
             mark(T_P);
         }
         B200_CUDA(cudaEventRecord(w.ev1, w.st));

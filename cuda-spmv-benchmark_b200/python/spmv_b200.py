@@ -117,7 +117,7 @@ C_SYMBOLS = [
     "b200_cg_scalars_bytes", "b200_cg_status_bytes", "b200_xchg_bytes", "b200_cg_max_partials",
     "b200_cg_residual_init", "b200_cg_spmv_dot", "b200_cg_update_xr", "b200_cg_update_p", "b200_cg_reduce",
     "b200_cg_update_p_push", "b200_cg_spmv_fused", "b200_cg_update_r", "b200_cg_halo_dir",
-    "b200_cg_finish_x", "b200_cg_spmv_fused_nx", "b200_cg_finish_x_depth", "b200_cg_set_xdepth", "b200_cg_update_px", "b200_cg_set_schedule", "b200_cg_set_pdl", "b200_cg_read_tail_times",
+    "b200_cg_finish_x", "b200_cg_spmv_fused_nx", "b200_cg_finish_x_depth", "b200_cg_set_xdepth", "b200_cg_update_px", "b200_cg_update_px_nx", "b200_cg_set_schedule", "b200_cg_set_pdl", "b200_cg_read_tail_times",
     "b200_csr_dot_partials_capacity",
     "b200_spmv_csr_dot", "b200_spmv_ellpack_dot", "b200_pcg_diag_inv", "b200_pcg_init", "b200_pcg_update_xr",
     "b200_pcg_update_p", "b200_bj_factor", "b200_bj_solve", "b200_pcg_update_xr_stored_z",
@@ -218,6 +218,7 @@ def load():
     L.b200_cg_spmv_fused_nx.argtypes = [C.POINTER(Band), vp, C.POINTER(vp), i32, vp, vp, vp, vp, C.POINTER(ReduceCtx), vp]
     L.b200_cg_finish_x_depth.argtypes = [ll, vp, C.POINTER(vp), i32, i32, i32, vp, vp]
     L.b200_cg_set_xdepth.argtypes = [i32]
+    L.b200_cg_update_px_nx.argtypes = [ll, vp, vp, vp, C.POINTER(vp), i32, vp, vp, vp]
     L.b200_cg_update_px.argtypes = [ll, vp, vp, vp, vp, vp]
     L.b200_cg_set_schedule.restype = None
     L.b200_cg_set_schedule.argtypes = [i32]

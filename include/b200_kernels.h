@@ -283,6 +283,11 @@ int b200_cg_finish_x(long long n, const void* d_scalars, const double* d_p0, con
  * :91-96 + axpy_kernel_device :59-66).  b200_cg_finish_x(only_if_converged = 1) closes the solve. */
 int b200_cg_update_px(long long n, const void* d_scalars, const double* d_r, double* d_p, double* d_x,
                       b200_stream stream);
+/* K3x with the x stream amortised over `depth` iterations, like b200_cg_spmv_fused_nx: p_new = r + beta p_old into
+ * a fresh direction buffer; nx = m > 0 also retires the m pending x updates (p_old and d_p_older[k] = the
+ * directions before it), oldest first.  b200_cg_finish_x_depth(only_if_converged = 1) closes the solve. */
+int b200_cg_update_px_nx(long long n, const void* d_scalars, const double* d_r, const double* d_p_old,
+                         const double* const* d_p_older, int nx, double* d_p_new, double* d_x, b200_stream stream);
 /* host engine: 1 = deferred-x schedule (default for the STENCIL5 path), 0 = classic 3-launch schedule;
  * the environment variable B200_CG_SCHEDULE=classic selects 0 at start-up */
 void b200_cg_set_schedule(int deferred_x);

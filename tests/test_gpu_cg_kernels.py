@@ -93,18 +93,18 @@ def test_cg_xdepth_bit_identical_to_classic(B, torch_cuda, restore_cg_defaults, 
     rng = np.random.default_rng(n)
     b, x0 = rng.standard_normal(N), rng.standard_normal(N)
     L.b200_cg_set_kernel(kernel)
-    for max_iters in (1000, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for tol, max_iters in [(1e-6, m) for m in (1000, 1, 2, 3, 4, 5, 6, 7, 8, 9)] + [(1e-4, 1000), (1e-2, 1000), (1e-1, 1000)]:
         L.b200_cg_set_schedule(0)
-        xc, sc, op = solve_device(B, b"stencil5-csr", hm, b, x0, max_iters=max_iters)
+        xc, sc, op = solve_device(B, b"stencil5-csr", hm, b, x0, tol=tol, max_iters=max_iters)
         op.contents.free()
         L.b200_cg_set_schedule(1)
         for depth in (1, 2, 3, 4):
             L.b200_cg_set_xdepth(depth)
-            xd, sd, op = solve_device(B, b"stencil5-csr", hm, b, x0, max_iters=max_iters)
+            xd, sd, op = solve_device(B, b"stencil5-csr", hm, b, x0, tol=tol, max_iters=max_iters)
             op.contents.free()
-            assert sd["iterations"] == sc["iterations"] and sd["converged"] == sc["converged"], (max_iters, depth)
-            assert sd["residual_norm"] == sc["residual_norm"], (max_iters, depth)
-            assert np.array_equal(xc, xd), (max_iters, depth)
+            assert sd["iterations"] == sc["iterations"] and sd["converged"] == sc["converged"], (tol, max_iters, depth)
+            assert sd["residual_norm"] == sc["residual_norm"], (tol, max_iters, depth)
+            assert np.array_equal(xc, xd), (tol, max_iters, depth)
 
 
 @pytest.mark.parametrize("n,P", [(81, 2), (64, 8), (130, 3), (512, 4)])
@@ -139,3 +139,31 @@ def test_cg_xdepth_virtual_ranks_bit_identical_to_classic(B, torch_cuda, restore
                 assert np.array_equal(got[0], ref[0]), (max_iters, depth)
     finally:
         L.b200_mgpu_finalize()
+
+
+@pytest.mark.parametrize("opname", [b"cusparse-csr", b"ellpack"])
+@pytest.mark.parametrize("n", [3, 81, 300])
+def test_cg_k3x_depth_bit_identical_to_classic_generic_operators(B, torch_cuda, restore_cg_defaults, n, opname):
+    """operators without a fused SpMV: the p update (K3x) writes a fresh direction buffer and retires the x updates
+    of the last `depth` iterations every depth-th launch; solves stopped by max_iters after 1..9 iterations leave
+    0..depth-1 updates pending (the K3x launch of the last iteration has run), converged ones 1..depth."""
+    L = restore_cg_defaults
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(n)
+    b, x0 = rng.standard_normal(N), rng.standard_normal(N)
+    for tol in (1e-6, 1e-3, 1e-1):  # converge after different iteration counts
+        for max_iters in (1000, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+            if tol != 1e-6 and max_iters != 1000:
+                continue
+            L.b200_cg_set_schedule(0)
+            xc, sc, op = solve_device(B, opname, hm, b, x0, tol=tol, max_iters=max_iters)
+            op.contents.free()
+            L.b200_cg_set_schedule(1)
+            for depth in (1, 2, 3, 4):
+                L.b200_cg_set_xdepth(depth)
+                xd, sd, op = solve_device(B, opname, hm, b, x0, tol=tol, max_iters=max_iters)
+                op.contents.free()
+                assert sd["iterations"] == sc["iterations"] and sd["converged"] == sc["converged"], (tol, max_iters, depth)
+                assert sd["residual_norm"] == sc["residual_norm"], (tol, max_iters, depth)
+                assert np.array_equal(xc, xd), (tol, max_iters, depth)
