@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -196,6 +197,48 @@ extern "C" int b200_mgpu_connect(const void* handles) {
 // per-rank solver workspace (cached between solves of the same shape)
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// ---- initial guess: is the caller's x0 all (+0.0)?  Then the device vector is cleared instead of uploaded.
+// x0 = 0 is the usual CG start (the reference's own CLIs pass zeros, cg_solver.cu:146-150), and at 20k x 20k
+// the upload of 3.2 GB of zeros is a fifth of the end-to-end time of a solve.  The scan runs on host threads
+// while the copy engine uploads b (the caller's buffers are not modified; bit patterns are compared, so -0.0
+// or a denormal counts as non-zero and the result is bit-identical either way).  A non-zero guess is
+// recognised within the first few elements: its cost is a few microseconds.  B200_SKIP_ZERO_X0=0 switches it off.
+std::atomic<long long> g_last_h2d_bytes{0};
+std::atomic<int> g_skip_zero_x0{-1};
+bool skip_zero_x0_enabled() {
+    int v = g_skip_zero_x0.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("B200_SKIP_ZERO_X0");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_skip_zero_x0.store(v, std::memory_order_relaxed);
+    }
+    return v == 1;
+}
+bool host_all_zero(const double* p, long long n, int max_threads) {
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
+    const long long head = std::min<long long>(n, 4096);
+    for (long long i = 0; i < head; i++)
+        if (q[i]) return false;
+    if (n == head) return true;
+    const long long block = 1 << 17;  // 1 MB between looks at the stop flag
+    int nt = (int)std::min<long long>(std::max(1, max_threads), (n - head + block - 1) / block);
+    std::atomic<bool> nonzero{false};
+    auto scan = [&](long long lo, long long hi) {
+        for (long long b0 = lo; b0 < hi && !nonzero.load(std::memory_order_relaxed); b0 += block) {
+            const long long b1 = std::min(hi, b0 + block);
+            uint64_t acc = 0;
+            for (long long i = b0; i < b1; i++) acc |= q[i];
+            if (acc) nonzero.store(true, std::memory_order_relaxed);
+        }
+    };
+    const long long per = (n - head + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(scan, head + t * per, std::min(n, head + (t + 1) * per));
+    scan(head, std::min(n, head + per));
+    for (auto& t : th) t.join();
+    return !nonzero.load();
+}
 
 struct RankWs {
     int rank = 0, dev = 0;
@@ -479,7 +522,14 @@ struct Engine {
         B200_CUDA(cudaMemsetAsync(w.scalars, 0, b200_cg_scalars_bytes(), w.st));
         memset((void*)w.status, 0, sizeof(HostStatus));
         B200_CUDA(cudaMemcpyAsync(w.b, b_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
-        B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
+        {
+            // x0: cleared on the device if the host vector is all zeros (scanned while b is on its way)
+            const int scan_threads = std::max(1, std::min(16, (int)std::thread::hardware_concurrency() / (int)std::max<size_t>(1, ws.ranks.size())));
+            const bool zero = skip_zero_x0_enabled() && host_all_zero(x_host + w.off, w.nl, scan_threads);
+            if (zero) B200_CUDA(cudaMemsetAsync(w.x, 0, (size_t)w.nl * sizeof(double), w.st));
+            else B200_CUDA(cudaMemcpyAsync(w.x, x_host + w.off, (size_t)w.nl * sizeof(double), cudaMemcpyHostToDevice, w.st));
+            g_last_h2d_bytes.fetch_add((zero ? 1 : 2) * w.nl * (long long)sizeof(double), std::memory_order_relaxed);
+        }
         const bool bj = pcg && precond == 2;
         if (pcg) {
             // untimed set-up like the uploads: dinv = 1 / diag(A) -- or the line factors of the block-Jacobi
@@ -728,6 +778,7 @@ struct Engine {
         const size_t L = ws.ranks.size();
         b_host = b_host_; x_host = x_host_; max_iters = max_iters_; tol = tol_; verbose = verbose_; timers = timers_; tag = tag_;
         if (pcg && !fused && g.world > 1) { fprintf(stderr, "[ERROR] multi-GPU PCG runs on the band kernels\n"); return 1; }
+        g_last_h2d_bytes.store(0);
         pt = PhaseTimer();
         pt.w = &ws.ranks[0];
         pt.on = timers != 0;
@@ -1049,6 +1100,15 @@ int solve_mgpu(MatrixData* mat, const double* b, double* x, CGConfigMultiGPU con
 // Per-phase event times (ms) and launch counts of the most recent solve that ran with
 // enable_detailed_timers: [0] unused, [1] K1 SpMV+p.Ap, [2] reduce p.Ap, [3] K2 x/r update + r.r,
 // [4] reduce r.r, [5] K3 p update, [6] halo push, [7] residual init, [8] reduce r0.r0.
+// zero-initial-guess detection on / off (default on, env B200_SKIP_ZERO_X0=0); returns the previous setting
+extern "C" int b200_cg_set_skip_zero_x0(int on) {
+    const int old = skip_zero_x0_enabled() ? 1 : 0;
+    g_skip_zero_x0.store(on ? 1 : 0, std::memory_order_relaxed);
+    return old;
+}
+// bytes the local ranks of the most recent solve uploaded (b, and x0 unless it was all zeros)
+extern "C" long long b200_last_h2d_bytes(void) { return g_last_h2d_bytes.load(); }
+
 extern "C" int b200_last_phase_times(double* ms9, int* count9) {
     for (int t = 0; t < T_N; t++) {
         if (ms9) ms9[t] = g_last.phase_ms[t];

@@ -451,3 +451,36 @@ def test_cg_operator_reinit_between_solves(B, orc, torch_cuda, n):
             assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-12
     finally:
         L.b200_cg_set_schedule(1)
+
+
+def test_cg_zero_initial_guess_is_not_uploaded(B, orc, torch_cuda):
+    """x0 all (+0.0): the engine scans the caller's vector (host threads, while b is uploaded) and clears the
+    device vector instead of uploading it -- same iterates bit for bit; anything else (a single non-zero at the
+    very end, -0.0) is uploaded as before.  b200_last_h2d_bytes counts what was copied."""
+    L = B.load()
+    n = 300
+    N = n * n
+    hm = B.HostMatrix.synthetic_stencil(n)
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(N)
+    old = L.b200_cg_set_skip_zero_x0(1)
+    try:
+        x_on, st_on, op = solve_device(B, b"stencil5-csr", hm, b, np.zeros(N))
+        assert L.b200_last_h2d_bytes() == 8 * N
+        op.contents.free()
+        L.b200_cg_set_skip_zero_x0(0)
+        x_off, st_off, op = solve_device(B, b"stencil5-csr", hm, b, np.zeros(N))
+        assert L.b200_last_h2d_bytes() == 16 * N
+        op.contents.free()
+        assert st_on["iterations"] == st_off["iterations"] and st_on["residual_norm"] == st_off["residual_norm"]
+        assert np.array_equal(x_on, x_off)
+        L.b200_cg_set_skip_zero_x0(1)
+        for x0 in (np.concatenate([np.zeros(N - 1), [1e-300]]), np.full(N, -0.0), np.concatenate([[3.0], np.zeros(N - 1)])):
+            x, st, op = solve_device(B, b"stencil5-csr", hm, b, x0)
+            assert L.b200_last_h2d_bytes() == 16 * N
+            op.contents.free()
+            xo, ro, _ = oracle_solve(orc, n, 1, b, x0)
+            assert st["iterations"] == ro["iterations"]
+            assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    finally:
+        L.b200_cg_set_skip_zero_x0(old)
