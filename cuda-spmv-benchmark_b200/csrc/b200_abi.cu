@@ -56,13 +56,15 @@ extern "C" unsigned long long b200_launch_count(void) { return g_launches.load()
 
 namespace {
 // programmatic dependent launch, bit 0: the small kernels of the loop (reduce, halo direction, finish_x),
-// bit 1: the STENCIL5 kernels.  B200_PDL=<0..3>, b200_cg_set_pdl().
+// bit 1: the STENCIL5 kernels, bit 2 (off by default): the BLAS-1 kernels K2 / K2r / K3 as well -- with the sweep
+// kernels in front of them that gains 2 us per iteration at 12.5 M rows (3.538 -> 3.505 ms) and still loses 1.3 %
+// at 400 M rows (93.05 -> 94.3 ms).  B200_PDL=<0..7>, b200_cg_set_pdl().
 std::atomic<int> g_pdl{-1};
 int pdl_mode() {
     int v = g_pdl.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("B200_PDL");
-        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : B200_PDL_DEFAULT;
+        v = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : B200_PDL_DEFAULT;
         g_pdl.store(v, std::memory_order_relaxed);
     }
     return v;
@@ -655,6 +657,11 @@ template <typename... KArgs, typename... Args>
 cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl_mode() & 4) ? 1 : 0;  // bit 2 (off by default): A/B switch for the statement above
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
@@ -723,7 +730,7 @@ int make_push(const b200_halo_push_args* h, long long n, const double* v, const 
 }
 }  // namespace
 
-extern "C" void b200_cg_set_pdl(int mode) { g_pdl.store(mode & 3, std::memory_order_relaxed); }
+extern "C" void b200_cg_set_pdl(int mode) { g_pdl.store(mode & 7, std::memory_order_relaxed); }
 
 extern "C" int b200_cg_max_partials(const b200_band* band) {
     int n = b200_stencil5_num_partials(band);
