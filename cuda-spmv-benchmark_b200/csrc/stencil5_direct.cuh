@@ -129,6 +129,13 @@ __device__ __forceinline__ double sweep_coef(const double* p) {
     return __ldg(p);
 #endif
 }
+// west / east neighbours of the fast path from the neighbouring lanes' centre elements (shuffle) instead of two
+// more (L1-hit) loads per vector: 11 instead of 15 load instructions per row in the fused modes.  Correct, and
+// slower (20k x 20k CG 92.95 -> 98.9 ms): the shuffles wait for the centre loads, and everything behind them in
+// program order waits with them -- the independent L1-hit loads are the cheaper way.  Kept as an A/B switch.
+#ifndef B200_SWEEP_SHFL
+#define B200_SWEEP_SHFL 0
+#endif
 #ifndef B200_SWEEP_TILES
 #define B200_SWEEP_TILES 2
 #endif
@@ -200,7 +207,23 @@ __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args 
 #pragma unroll
     for (int k = 0; k < SWEEP_TILES; k++) {
         const unsigned int lr = row_lo + k * 256u + threadIdx.x;
+#if B200_SWEEP_SHFL
+        // centre element of every valid row first (all lanes take part in the shuffles: no early exit)
+        const bool valid = lr < nloc;
+        double poC = 0.0, xC = 0.0;
+        if (valid) {
+            if (st_fused(MODE)) {
+                poC = __ldg(a.x + lr);  // p_old
+                xC = fma(beta, poC, __ldg(a.r + lr));
+            } else {
+                xC = __ldg(a.x + lr);
+            }
+        }
+        double xW = __shfl_up_sync(0xffffffffu, xC, 1), xE = __shfl_down_sync(0xffffffffu, xC, 1);
+        if (!valid) continue;
+#else
         if (lr >= nloc) break;
+#endif
         const unsigned int q = (j_off + lr) / n;
         const unsigned int i = i_off + q, j = j_off + lr - q * n;
         const bool interior = (i >= 1) && (i + 2 <= n) && (j >= 1) && (j + 2 <= n);
@@ -208,6 +231,23 @@ __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args 
             // ---------------------------------------------------------------- every neighbour is a local element
             const double* v = a.values + (a.base0 + (long long)i * a.row_stride + 5 * (long long)j);
             const double vN = sweep_coef(v), vW = sweep_coef(v + 1), vC = sweep_coef(v + 2), vE = sweep_coef(v + 3), vS = sweep_coef(v + 4);
+#if B200_SWEEP_SHFL
+            double xN, xS;
+            const unsigned int lane = threadIdx.x & 31u;
+            if (st_fused(MODE)) {
+                const double* pr = a.r + lr;
+                const double* pp = a.x + lr;
+                if (lane == 0) xW = fma(beta, __ldg(pp - 1), __ldg(pr - 1));
+                if (lane == 31) xE = fma(beta, __ldg(pp + 1), __ldg(pr + 1));
+                xN = fma(beta, __ldg(pp - (long long)n), __ldg(pr - (long long)n));
+                xS = fma(beta, __ldg(pp + n), __ldg(pr + n));
+            } else {
+                const double* px = a.x + lr;
+                if (lane == 0) xW = __ldg(px - 1);
+                if (lane == 31) xE = __ldg(px + 1);
+                xN = __ldg(px - (long long)n); xS = __ldg(px + n);
+            }
+#else
             double xW, xC, xE, xN, xS, poC = 0.0;
             if (st_fused(MODE)) {
                 const double* pr = a.r + lr;
@@ -223,6 +263,7 @@ __global__ void __launch_bounds__(256) stencil5_sweep_kernel(const Stencil5Args 
                 xC = __ldg(px); xW = __ldg(px - 1); xE = __ldg(px + 1);
                 xN = __ldg(px - (long long)n); xS = __ldg(px + n);
             }
+#endif
             double t = vC * xC;
             t = fma(vW, xW, t);
             t = fma(vE, xE, t);
