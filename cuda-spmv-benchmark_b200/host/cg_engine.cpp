@@ -19,6 +19,11 @@
 // status word kLag iterations behind (the reference does a blocking 4-byte D2H every iteration,
 // cg_solver.cu:598-599).
 //
+// Schedules (all bit-identical to each other): classic K1 / K2 / K3; deferred x on the STENCIL5 path (the
+// direction update rides inside the SpMV launch, the x updates of the last `x_depth()` iterations are retired
+// together by every x_depth()-th of those launches: 106 B/row per iteration at depth 4); K3x with the same depth
+// for operators without a fused SpMV.  An all-zero initial guess is recognised on the host and not uploaded.
+//
 // Every local rank is driven by its own host thread (one enqueue thread per GPU when one process
 // drives several devices, the north-star topology).  Exchange sequence numbers are counted on the
 // device, so the threads -- or processes -- need not agree on how many no-op iterations they enqueue
