@@ -1105,6 +1105,10 @@ int solve_mgpu(MatrixData* mat, const double* b, double* x, CGConfigMultiGPU con
 // Per-phase event times (ms) and launch counts of the most recent solve that ran with
 // enable_detailed_timers: [0] unused, [1] K1 SpMV+p.Ap, [2] reduce p.Ap, [3] K2 x/r update + r.r,
 // [4] reduce r.r, [5] K3 p update, [6] halo push, [7] residual init, [8] reduce r0.r0.
+// the host-side scan on its own (no GPU involved): 1 if all n doubles are +0.0 bit patterns
+extern "C" int b200_host_all_zero(const double* p, long long n, int threads) {
+    return (p != nullptr && n >= 0 && host_all_zero(p, n, threads)) ? 1 : 0;
+}
 // zero-initial-guess detection on / off (default on, env B200_SKIP_ZERO_X0=0); returns the previous setting
 extern "C" int b200_cg_set_skip_zero_x0(int on) {
     const int old = skip_zero_x0_enabled() ? 1 : 0;

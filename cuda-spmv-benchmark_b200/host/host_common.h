@@ -95,6 +95,7 @@ void b200_get_tuning(int* variant, int* rows_per_item);
 int b200_last_phase_times(double* ms9, int* count9);
 long long b200_last_h2d_bytes(void);
 int b200_cg_set_skip_zero_x0(int on);
+int b200_host_all_zero(const double* p, long long n, int threads);
 int b200_pcg_set_preconditioner(int kind);
 int b200_last_tail_times(double* ms8, int* count8);
 int b200_last_gap_times(double* ms8);

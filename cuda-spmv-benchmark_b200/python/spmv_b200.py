@@ -135,7 +135,7 @@ C_SYMBOLS = [
     # extensions (host/host_common.h)
     "b200_operator_band", "b200_mgpu_init_single_process", "b200_mgpu_init_rank", "b200_mgpu_connect",
     "b200_mgpu_world", "b200_mgpu_rank", "b200_mgpu_finalize", "b200_synthetic_stencil", "b200_set_tuning",
-    "b200_get_tuning", "b200_last_phase_times", "b200_last_h2d_bytes", "b200_cg_set_skip_zero_x0", "b200_last_tail_times", "b200_last_gap_times", "b200_pcg_set_preconditioner", "b200_mgpu_halo_probe", "b200_load_matrix_market_device", "b200_operator_init_device_coo",
+    "b200_get_tuning", "b200_last_phase_times", "b200_last_h2d_bytes", "b200_cg_set_skip_zero_x0", "b200_host_all_zero", "b200_last_tail_times", "b200_last_gap_times", "b200_pcg_set_preconditioner", "b200_mgpu_halo_probe", "b200_load_matrix_market_device", "b200_operator_init_device_coo",
     "b200_operator_device_csr", "b200_free_device", "b200_copy_to_host", "b200_host_node_of_device",
     "b200_host_alloc_near", "b200_host_free",
 ]
@@ -275,6 +275,7 @@ def load():
     L.b200_last_h2d_bytes.restype = ll
     L.b200_last_h2d_bytes.argtypes = []
     L.b200_cg_set_skip_zero_x0.argtypes = [i32]
+    L.b200_host_all_zero.argtypes = [vp, ll, i32]
     L.b200_last_tail_times.argtypes = [C.POINTER(dbl), C.POINTER(i32)]
     L.b200_last_gap_times.argtypes = [C.POINTER(dbl)]
     L.b200_pcg_set_preconditioner.argtypes = [i32]

@@ -258,3 +258,32 @@ def test_csr_cache_is_keyed_on_the_matrix_not_only_its_shape(B, orc):
     bad["col"][5] = N + 3
     hb = B.HostMatrix.from_entries(N, N, bad, grid_size=n)
     assert L.build_csr_struct(hb.ptr()) != 0
+
+
+def test_host_zero_guess_scan(B):
+    """the host-side scan behind the zero-initial-guess path (host/cg_engine.cpp: host_all_zero): a wrong 'all
+    zero' would silently drop the caller's initial guess, so every position class is probed -- the serial head,
+    the first / last element of every thread's range, block boundaries, the very last element -- and -0.0 and
+    denormals must count as non-zero (bit patterns are compared: the cleared device vector must be identical)."""
+    import numpy as np
+    L = B.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 4095, 4096, 4097, 131072 + 4096, 131072 + 4097, 1_000_003, 3_500_000):
+        for threads in (1, 3, 16):
+            x = np.zeros(max(n, 1))
+            assert L.b200_host_all_zero(x.ctypes.data, n, threads) == 1, (n, threads)
+            if n == 0:
+                continue
+            probes = {0, n - 1, n // 2, min(n - 1, 4095), min(n - 1, 4096), min(n - 1, 4096 + 131072 - 1), min(n - 1, 4096 + 131072)}
+            probes |= {int(v) for v in rng.integers(0, n, size=6)}
+            for nt in (threads,):
+                per = (max(n - 4096, 0) + nt - 1) // nt if n > 4096 else 0
+                for t in range(nt):
+                    if per:
+                        probes |= {min(n - 1, 4096 + t * per), min(n - 1, 4096 + (t + 1) * per - 1)}
+            for i in sorted(probes):
+                for v in (1.0, -0.0, 5e-324, float("nan")):
+                    x[i] = v
+                    assert L.b200_host_all_zero(x.ctypes.data, n, threads) == 0, (n, threads, i, v)
+                    x[i] = 0.0
+            assert L.b200_host_all_zero(x.ctypes.data, n, threads) == 1
